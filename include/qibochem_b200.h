@@ -1,0 +1,115 @@
+/*
+ * qibochem_b200 -- C ABI of the B200-native UCC-energy hot path.
+ *
+ * This is the drop-in boundary for ONE path of qiboteam/qibochem (reference citations are relative to the
+ * reference checkout): HF basis state -> UCC Pauli rotations exp(-i phi P / 2) on a complex128 state vector ->
+ * Hamiltonian expectation sum_k c_k <psi|P_k|psi>, exact and sampled (QWC-grouped).  The reference reaches this
+ * arithmetic through qibo's object protocol (Circuit.__call__, SymbolicHamiltonian.expectation /
+ * .expectation_from_samples), not through an FFI; each entry point names the reference call it replaces.
+ *
+ * Conventions
+ *   - All masks are in INDEX-BIT positions of the local shard: qubit q of an n-qubit register is bit (n-1-q)
+ *     (qibo puts qubit 0 on the most significant index bit).  x = X|Y sites, z = Z|Y sites of a Pauli string.
+ *   - (P psi)_i = (-i)^{popcount(x&z)} * (-1)^{popcount(i&z)} * psi_{i^x}.
+ *   - A rotation with angle phi applies  psi <- cos(phi/2) psi - i sin(phi/2) P psi   (== qibochem's
+ *     _expi_pauli(n, P, theta) with phi = -2 theta, src/qibochem/ansatz/_ansatz.py:55-92).
+ *   - Every function returns 0 on success, non-zero on error; qc_last_error() returns the message of the last
+ *     failure on the calling thread.  There is no CPU fallback: without a CUDA device every call fails.
+ *   - Host arrays are borrowed for the duration of the call.  A handle is not thread-safe.
+ *   - A handle owns ONE shard of 2^n_local amplitudes on one GPU.  Multi-GPU runs use one handle (one process)
+ *     per GPU; the host layer moves index bits between "global" (rank) and local positions with
+ *     qc_swap_with_peer and folds the rank-dependent signs of global Z factors into angles / coefficients.
+ */
+#ifndef QIBOCHEM_B200_H
+#define QIBOCHEM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct qc_state qc_state;
+
+/* ---- library / device ------------------------------------------------------------------------------------ */
+const char* qc_last_error(void);
+int qc_version(void);
+/* Number of visible CUDA devices (0 and an error if none). */
+int qc_device_count(int* count);
+
+/* ---- state life cycle  (replaces: allocation of the state inside qibo Circuit.__call__) ------------------- */
+/* stream: a cudaStream_t created by the caller in the same CUDA context (e.g. torch's current stream), or NULL
+ * for a stream owned by the handle.  Allocates 16 * 2^n_local bytes of HBM. */
+int qc_create(int device, int n_local_qubits, void* stream, qc_state** out);
+int qc_destroy(qc_state* h);
+int qc_num_qubits(const qc_state* h);
+/* Raw device pointer of the shard (complex128[2^n_local]); for the host layer's NCCL / IPC plumbing only. */
+int qc_state_device_ptr(qc_state* h, void** ptr);
+int qc_synchronize(qc_state* h);
+
+/* ---- K0: basis state  (replaces hf_circuit's X-gate passes, src/qibochem/ansatz/ansatz.py:276-282) --------- */
+/* psi <- 0; if has_one, psi[index] <- 1.  (A sharded caller passes has_one=1 only on the owning rank.) */
+int qc_set_basis_state(qc_state* h, uint64_t index, int has_one);
+
+/* ---- K1: Pauli rotations  (replaces the 16-40 gate passes per _expi_pauli, _ansatz.py:80-92, executed by
+ *      qibo's backend gate loop reached from Circuit.__call__) ---------------------------------------------- */
+/* Applies R rotations IN ORDER.  Consecutive strings that share an x-mask and commute are fused into one pass
+ * (the 8 strings of a JW double excitation always do).  n_passes_out (may be NULL) receives the number of
+ * full-state passes actually launched. */
+int qc_apply_pauli_rotations(qc_state* h, size_t R, const uint64_t* xmask, const uint64_t* zmask,
+                             const double* angle, int* n_passes_out);
+
+/* ---- K2: exact expectation  (replaces SymbolicHamiltonian.expectation(circuit), called e.g. at
+ *      tests/test_ansatz.py:131, examples/ucc_example1.py:45) ------------------------------------------------ */
+/* energy_out <- sum_k coeff[k] * Re<psi|P_k|psi> over this shard (no constant term; the host adds it and
+ * all-reduces across shards).  per_term (may be NULL) receives the T individual values Re<psi|P_k|psi>.
+ * Terms are grouped by x-mask; every group costs one read-only sweep of the shard. n_sweeps_out may be NULL. */
+int qc_expectation(qc_state* h, size_t T, const uint64_t* xmask, const uint64_t* zmask, const double* coeff,
+                   double* energy_out, double* per_term, int* n_sweeps_out);
+/* <psi|psi> over this shard. */
+int qc_norm2(qc_state* h, double* out);
+
+/* ---- K5: sampling in a product Pauli basis (replaces Circuit.__call__(nshots=) with gates.M(q, basis=...),
+ *      src/qibochem/measurement/result.py:106-114) ---------------------------------------------------------- */
+/* Draws n_shots indices i with probability |<i|B|psi>|^2 where B rotates the qubits in x_basis_mask with H and
+ * those in y_basis_mask with H S^dagger (psi itself is left untouched: the rotation runs on a scratch copy).
+ * samples_out: DEVICE or HOST buffer of n_shots uint64 (flag samples_on_device).  Philox4x32-10, counter = shot
+ * index + shot_offset, so shards / repeated calls can draw disjoint streams.  total_prob_out may be NULL. */
+int qc_sample(qc_state* h, uint64_t x_basis_mask, uint64_t y_basis_mask, size_t n_shots, uint64_t seed,
+              uint64_t shot_offset, uint64_t* samples_out, int samples_on_device, double* total_prob_out);
+
+/* ---- K3: integer shot statistics (replaces the Python loops of qibo's expectation_from_samples reached from
+ *      src/qibochem/measurement/result.py:38-54; bit-exact) -------------------------------------------------- */
+/* S_out[j] = sum_s weight_s * (-1)^{popcount(samples[s] & zmask[j])}, weight_s = counts[s] or 1 if counts==NULL.
+ * samples/counts: device or host buffers according to on_device. */
+int qc_parity_sums(qc_state* h, const uint64_t* samples, const int64_t* counts, size_t n, int on_device,
+                   const uint64_t* zmask, size_t J, int64_t* S_out);
+/* Histogram of samples over `keep_mask` bits (result.frequencies()): keys_out/counts_out are HOST buffers of
+ * capacity `cap`; keys are the compacted bit patterns (pext(sample, keep_mask)), ascending.  n_unique_out
+ * receives the number of distinct keys (error if > cap). */
+int qc_frequencies(qc_state* h, const uint64_t* samples, size_t n, int on_device, uint64_t keep_mask,
+                   uint64_t* keys_out, int64_t* counts_out, size_t cap, size_t* n_unique_out);
+
+/* ---- host <-> device copies of amplitudes (tests, checkpoints; n <= ~30) ----------------------------------- */
+/* interleaved (re, im) doubles */
+int qc_copy_state_to_host(qc_state* h, double* out, uint64_t offset, uint64_t count);
+int qc_copy_state_from_host(qc_state* h, const double* in, uint64_t offset, uint64_t count);
+
+/* ---- K4: global <-> local index-bit exchange between two shards over NVLink peer memory -------------------- */
+/* 64-byte CUDA IPC handle of this shard, to be passed to the partner process. */
+int qc_ipc_export(qc_state* h, unsigned char handle[64]);
+int qc_ipc_open(qc_state* h, const unsigned char handle[64], void** peer_ptr);
+int qc_ipc_close(qc_state* h, void* peer_ptr);
+/* Swaps the half of this shard where `local_bit` == 1 - my_side with the partner's half where `local_bit` ==
+ * my_side ... see DESIGN.md "K4".  Each rank of the pair moves one half of the exchanged elements: `part` in
+ * {0,1} selects which. Caller brackets the call with a cross-rank barrier on both sides. */
+int qc_swap_with_peer(qc_state* h, void* peer_ptr, int local_bit, int my_side, int part);
+/* Same exchange inside ONE process between two handles' shards (single-GPU emulation of two ranks for tests, or
+ * a single process driving peer-enabled GPUs). */
+int qc_swap_local_pair(qc_state* lo, qc_state* hi, int local_bit);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

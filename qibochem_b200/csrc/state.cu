@@ -1,0 +1,203 @@
+// State life cycle, K0 (basis state), host<->device copies, norm.
+#include "common.cuh"
+
+namespace qc {
+
+static thread_local std::string g_last_error;
+void set_error(const std::string& msg) { g_last_error = msg; }
+
+int Arena::ensure(size_t bytes) {
+    if (bytes <= cap) return 0;
+    size_t ncap = cap ? cap : (1u << 16);
+    while (ncap < bytes) ncap *= 2;
+    release();
+    QC_CHECK(cudaMallocHost(&host, ncap));
+    QC_CHECK(cudaMalloc(&dev, ncap));
+    cap = ncap;
+    return 0;
+}
+void Arena::release() {
+    if (host) cudaFreeHost(host);
+    if (dev) cudaFree(dev);
+    host = dev = nullptr;
+    cap = 0;
+}
+
+__global__ void set_one_kernel(double2* psi, uint64_t index) { psi[index] = make_double2(1.0, 0.0); }
+
+__global__ void __launch_bounds__(kThreads) norm2_kernel(const double2* __restrict__ psi, uint64_t dim,
+                                                         double* __restrict__ partials) {
+    double acc = 0.0;
+    for (uint64_t i = (uint64_t)blockIdx.x * kThreads + threadIdx.x; i < dim; i += (uint64_t)gridDim.x * kThreads) {
+        const double2 a = psi[i];
+        acc += a.x * a.x + a.y * a.y;
+    }
+    const double t = block_sum(acc);
+    if (threadIdx.x == 0) partials[blockIdx.x] = t;
+}
+
+// out[g] (+)= sum_b partials[g * stride + b], one CTA per g, fixed summation order.
+__global__ void __launch_bounds__(kThreads) fold_partials_kernel(const double* __restrict__ partials, int nb,
+                                                                 int stride, double* __restrict__ out) {
+    const double* p = partials + (size_t)blockIdx.x * stride;
+    double acc = 0.0;
+    for (int b = threadIdx.x; b < nb; b += kThreads) acc += p[b];
+    const double t = block_sum(acc);
+    if (threadIdx.x == 0) out[blockIdx.x] = t;
+}
+
+int fold_partials(qc_state* h, const double* partials, int ngroups, int nb, int stride, double* out) {
+    fold_partials_kernel<<<ngroups, kThreads, 0, h->stream>>>(partials, nb, stride, out);
+    QC_CHECK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace qc
+
+int qc_state::ensure_partials(size_t doubles) {
+    if (doubles <= partials_cap) return 0;
+    if (d_partials) cudaFree(d_partials);
+    d_partials = nullptr;
+    partials_cap = 0;
+    QC_CHECK(cudaMalloc(&d_partials, doubles * sizeof(double)));
+    partials_cap = doubles;
+    return 0;
+}
+int qc_state::ensure_out(size_t doubles) {
+    if (doubles <= out_cap) return 0;
+    if (d_out) cudaFree(d_out);
+    if (h_out) cudaFreeHost(h_out);
+    d_out = h_out = nullptr;
+    out_cap = 0;
+    size_t ncap = 1024;
+    while (ncap < doubles) ncap *= 2;
+    QC_CHECK(cudaMalloc(&d_out, ncap * sizeof(double)));
+    QC_CHECK(cudaMallocHost(&h_out, ncap * sizeof(double)));
+    out_cap = ncap;
+    return 0;
+}
+
+extern "C" {
+
+const char* qc_last_error(void) { return qc::g_last_error.c_str(); }
+int qc_version(void) { return 100; }
+
+int qc_device_count(int* count) {
+    QC_REQUIRE(count != nullptr, "qc_device_count: null pointer");
+    *count = 0;
+    QC_CHECK(cudaGetDeviceCount(count));
+    QC_REQUIRE(*count > 0, "qc_device_count: no CUDA device visible (there is no CPU fallback)");
+    return 0;
+}
+
+int qc_create(int device, int n_local_qubits, void* stream, qc_state** out) {
+    QC_REQUIRE(out != nullptr, "qc_create: null out pointer");
+    QC_REQUIRE(n_local_qubits >= 1 && n_local_qubits <= 40, "qc_create: n_local_qubits must be in [1, 40]");
+    int count = 0;
+    if (qc_device_count(&count)) return 1;
+    QC_REQUIRE(device >= 0 && device < count, "qc_create: bad device index");
+    QC_CHECK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    QC_CHECK(cudaGetDeviceProperties(&prop, device));
+    QC_REQUIRE(prop.major >= 10, "qc_create: this library is built for sm_100a (B200) only");
+    qc_state* h = new qc_state();
+    h->device = device;
+    h->n = n_local_qubits;
+    h->dim = 1ull << n_local_qubits;
+    h->sm_count = prop.multiProcessorCount;
+    if (stream) {
+        h->stream = (cudaStream_t)stream;
+    } else {
+        cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) {
+            delete h;
+            qc::set_error(std::string("cudaStreamCreate failed: ") + cudaGetErrorString(e));
+            return 1;
+        }
+        h->owns_stream = true;
+    }
+    cudaError_t e = cudaMalloc(&h->psi, h->dim * sizeof(double2));
+    if (e != cudaSuccess) {
+        qc::set_error(std::string("qc_create: cudaMalloc of the state failed: ") + cudaGetErrorString(e));
+        if (h->owns_stream) cudaStreamDestroy(h->stream);
+        delete h;
+        return 1;
+    }
+    *out = h;
+    return 0;
+}
+
+int qc_destroy(qc_state* h) {
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    if (h->psi) cudaFree(h->psi);
+    if (h->scratch_psi) cudaFree(h->scratch_psi);
+    if (h->d_partials) cudaFree(h->d_partials);
+    if (h->d_out) cudaFree(h->d_out);
+    if (h->h_out) cudaFreeHost(h->h_out);
+    h->arena.release();
+    if (h->owns_stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return 0;
+}
+
+int qc_num_qubits(const qc_state* h) { return h ? h->n : -1; }
+
+int qc_state_device_ptr(qc_state* h, void** ptr) {
+    QC_REQUIRE(h && ptr, "qc_state_device_ptr: null argument");
+    *ptr = h->psi;
+    return 0;
+}
+
+int qc_synchronize(qc_state* h) {
+    QC_REQUIRE(h, "qc_synchronize: null handle");
+    QC_CHECK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int qc_set_basis_state(qc_state* h, uint64_t index, int has_one) {
+    QC_REQUIRE(h, "qc_set_basis_state: null handle");
+    QC_REQUIRE(!has_one || index < h->dim, "qc_set_basis_state: index out of range");
+    QC_CHECK(cudaSetDevice(h->device));
+    QC_CHECK(cudaMemsetAsync(h->psi, 0, h->dim * sizeof(double2), h->stream));
+    if (has_one) {
+        qc::set_one_kernel<<<1, 1, 0, h->stream>>>(h->psi, index);
+        QC_CHECK(cudaGetLastError());
+    }
+    return 0;
+}
+
+int qc_norm2(qc_state* h, double* out) {
+    QC_REQUIRE(h && out, "qc_norm2: null argument");
+    QC_CHECK(cudaSetDevice(h->device));
+    const int nb = qc::grid_for(h->dim, 4, h->sm_count);
+    if (h->ensure_partials(nb) || h->ensure_out(1)) return 1;
+    qc::norm2_kernel<<<nb, qc::kThreads, 0, h->stream>>>(h->psi, h->dim, h->d_partials);
+    QC_CHECK(cudaGetLastError());
+    if (qc::fold_partials(h, h->d_partials, 1, nb, nb, h->d_out)) return 1;
+    QC_CHECK(cudaMemcpyAsync(h->h_out, h->d_out, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    QC_CHECK(cudaStreamSynchronize(h->stream));
+    *out = h->h_out[0];
+    return 0;
+}
+
+int qc_copy_state_to_host(qc_state* h, double* out, uint64_t offset, uint64_t count) {
+    QC_REQUIRE(h && out, "qc_copy_state_to_host: null argument");
+    QC_REQUIRE(offset + count <= h->dim, "qc_copy_state_to_host: range out of bounds");
+    QC_CHECK(cudaSetDevice(h->device));
+    QC_CHECK(cudaMemcpyAsync(out, h->psi + offset, count * sizeof(double2), cudaMemcpyDeviceToHost, h->stream));
+    QC_CHECK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int qc_copy_state_from_host(qc_state* h, const double* in, uint64_t offset, uint64_t count) {
+    QC_REQUIRE(h && in, "qc_copy_state_from_host: null argument");
+    QC_REQUIRE(offset + count <= h->dim, "qc_copy_state_from_host: range out of bounds");
+    QC_CHECK(cudaSetDevice(h->device));
+    QC_CHECK(cudaMemcpyAsync(h->psi + offset, in, count * sizeof(double2), cudaMemcpyHostToDevice, h->stream));
+    QC_CHECK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,21 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a B200 (run with `-m gpu` on the GPU box)")
+
+
+@pytest.fixture(scope="session")
+def native_lib():
+    """Builds (if stale) and loads the C-ABI library.  Loading works without a GPU; compute calls do not."""
+    from qibochem_b200 import _native, build_native
+
+    build_native.build()
+    return _native.load()

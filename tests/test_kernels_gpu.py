@@ -1,0 +1,267 @@
+"""GPU parity tests of the kernels, called through the C ABI, against the CPU oracle on the same seeded inputs.
+
+Tolerances: complex128 amplitudes <= 1e-12 max-abs, energies <= 1e-10 (north_star: 1e-10 Ha); integers bit-exact."""
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+AMP_TOL = 1e-12
+E_TOL = 1e-10
+
+
+@pytest.fixture(scope="module")
+def DeviceState(native_lib):
+    from qibochem_b200.engine import DeviceState as DS
+
+    return DS
+
+
+def random_state(n, seed):
+    rng = np.random.default_rng(seed)
+    psi = rng.normal(size=2**n) + 1j * rng.normal(size=2**n)
+    return psi / np.linalg.norm(psi)
+
+
+def random_string_masks(n, rng, kind="any"):
+    """Random Pauli string as (x, z) masks."""
+    if kind == "diag":
+        x = 0
+    elif kind == "low":
+        x = int(rng.integers(1, min(32, 2**n)))
+    elif kind == "high":
+        x = int(rng.integers(1, 2**n)) | (1 << (n - 1))
+    else:
+        x = int(rng.integers(0, 2**n))
+    z = int(rng.integers(0, 2**n))
+    return x, z
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 6, 9, 12])
+def test_basis_state_and_copy(DeviceState, n):
+    with DeviceState(n) as st:
+        idx = (1 << n) - 1 if n < 3 else 5
+        st.set_basis_state(idx)
+        v = st.to_numpy()
+        ref = np.zeros(2**n, dtype=complex)
+        ref[idx] = 1
+        assert np.array_equal(v, ref)
+        assert st.norm2() == 1.0
+        psi = random_state(n, n)
+        st.from_numpy(psi)
+        assert np.array_equal(st.to_numpy(), psi)
+        assert abs(st.norm2() - 1.0) < 1e-13
+
+
+@pytest.mark.parametrize("n", [1, 2, 4, 5, 6, 8, 11, 14])
+@pytest.mark.parametrize("kind", ["any", "diag", "low", "high"])
+def test_single_rotations_match_oracle(DeviceState, n, kind):
+    rng = np.random.default_rng(100 * n + len(kind))
+    psi = random_state(n, 7 * n + 1)
+    with DeviceState(n) as st:
+        st.from_numpy(psi)
+        ref = psi.copy()
+        xs, zs, phis = [], [], []
+        for _ in range(6):
+            x, z = random_string_masks(n, rng, kind)
+            phi = float(rng.uniform(-np.pi, np.pi))
+            xs.append(x), zs.append(z), phis.append(phi)
+            ref = O.apply_pauli_rotation(ref, x, z, phi)
+        st.apply_pauli_rotations(xs, zs, phis)
+        assert np.abs(st.to_numpy() - ref).max() < AMP_TOL
+
+
+@pytest.mark.parametrize("n", [4, 6, 10, 13])
+def test_fused_runs_match_sequential_oracle(DeviceState, n):
+    """Runs of commuting same-x strings (like the 8 strings of a JW double) fuse into one pass."""
+    rng = np.random.default_rng(n)
+    psi = random_state(n, 3 * n)
+    xs, zs, phis = [], [], []
+    for _ in range(5):
+        x = int(rng.integers(1, 2**n))
+        z0 = int(rng.integers(0, 2**n))
+        members = [z0]
+        for _ in range(40):
+            dz = int(rng.integers(0, 2**n)) & (x | int(rng.integers(0, 2**n)) & 0x7)
+            if bin(x & dz).count("1") % 2 == 0 and (z0 ^ dz) not in members:
+                members.append(z0 ^ dz)
+            if len(members) == 8:
+                break
+        for z in members:
+            xs.append(x), zs.append(z), phis.append(float(rng.uniform(-1, 1)))
+    # and a diagonal run
+    for _ in range(6):
+        xs.append(0), zs.append(int(rng.integers(1, 2**n)) & 0x3F), phis.append(float(rng.uniform(-1, 1)))
+    ref = psi.copy()
+    for x, z, p in zip(xs, zs, phis):
+        ref = O.apply_pauli_rotation(ref, x, z, p)
+    with DeviceState(n) as st:
+        st.from_numpy(psi)
+        passes = st.apply_pauli_rotations(xs, zs, phis)
+        assert passes < len(xs)
+        assert np.abs(st.to_numpy() - ref).max() < AMP_TOL
+
+
+def test_ucc_double_is_one_pass_and_matches_gate_path(DeviceState):
+    """HF + JW double excitation: mask path on the GPU == the reference's gate-by-gate program in the oracle."""
+    n, ne, theta = 6, 2, 0.3173
+    gates = O.hf_gates(n, ne) + O.ucc_gates([0, 1, 4, 5], theta) + O.ucc_gates([1, 3], -0.77)
+    ref = O.run_gates(n, gates)
+    xs, zs, phis = [], [], []
+    for exc, th in (([0, 1, 4, 5], theta), ([1, 3], -0.77)):
+        for string, coeff in O.ucc_pauli_terms(exc):
+            x, z = O.pauli_masks(n, string)
+            xs.append(x), zs.append(z), phis.append((2j * coeff * th).real)
+    with DeviceState(n) as st:
+        st.set_basis_state(((1 << ne) - 1) << (n - ne))
+        passes = st.apply_pauli_rotations(xs, zs, phis)
+        assert passes == 2  # 8 strings of the double -> 1 pass, 2 strings of the single -> 1 pass
+        assert np.abs(st.to_numpy() - ref).max() < AMP_TOL
+
+
+@pytest.mark.parametrize("n", [1, 2, 4, 5, 6, 9, 12, 15])
+def test_expectation_matches_oracle(DeviceState, n):
+    rng = np.random.default_rng(n)
+    psi = random_state(n, 11 * n)
+    T = 60
+    xs, zs = [], []
+    for k in range(T):
+        kind = ["any", "diag", "low", "high"][k % 4]
+        x, z = random_string_masks(n, rng, kind)
+        if k % 5 == 0 and xs:
+            x = xs[-1]  # repeated x-masks form groups
+        xs.append(x), zs.append(z)
+    cs = rng.normal(size=T)
+    ref_terms = np.array([np.vdot(psi, O.apply_pauli(psi, x, z)).real for x, z in zip(xs, zs)])
+    ref = float(np.dot(cs, ref_terms))
+    with DeviceState(n) as st:
+        st.from_numpy(psi)
+        e = st.expectation(xs, zs, cs)
+        assert abs(e - ref) < E_TOL
+        assert st.last_sweeps <= len(set(xs))
+        e2, per = st.expectation(xs, zs, cs, per_term=True)
+        assert np.abs(per - ref_terms).max() < E_TOL
+        assert abs(e2 - ref) < E_TOL
+
+
+def test_expectation_large_group_is_split(DeviceState):
+    n = 11
+    rng = np.random.default_rng(5)
+    psi = random_state(n, 2)
+    zs = rng.choice(2**n, size=1500, replace=False)
+    xs = np.zeros(1500, dtype=np.uint64)
+    cs = rng.normal(size=1500)
+    ref = O.expectation_masks(psi, xs, zs, cs)
+    with DeviceState(n) as st:
+        st.from_numpy(psi)
+        assert abs(st.expectation(xs, zs, cs) - ref) < E_TOL
+        assert st.last_sweeps == 2
+
+
+def test_h2_energies_from_doc_fixture(DeviceState):
+    """Known answers of the reference docs (hamiltonian.rst:59, ansatz.rst:73,80) through K0/K1/K2."""
+    from tests.fixtures import H2_JW_TERMS, masks_from_terms
+
+    n = 4
+    const, xs, zs, cs = masks_from_terms(n, H2_JW_TERMS)
+    with DeviceState(n) as st:
+        st.set_basis_state(0b1100)
+        assert abs(const + st.expectation(xs, zs, cs) - (-1.11628373627429)) < 1e-13
+        st.set_basis_state(0)
+        assert abs(const + st.expectation(xs, zs, cs) - 0.7074183344740923) < 1e-13
+        # UCCD scan reaches the FCI energy of the fixture
+        rx, rz, rc = [], [], []
+        for string, coeff in O.ucc_pauli_terms([0, 1, 2, 3]):
+            x, z = O.pauli_masks(n, string)
+            rx.append(x), rz.append(z), rc.append(coeff)
+        best = 0.0
+        for th in np.linspace(0.11, 0.12, 41):
+            st.set_basis_state(0b1100)
+            st.apply_pauli_rotations(rx, rz, [(2j * c * th).real for c in rc])
+            best = min(best, const + st.expectation(xs, zs, cs))
+        assert abs(best - (-1.1371622544371)) < 2e-7
+
+
+@pytest.mark.parametrize("n_shots", [1, 31, 1000, 100_003])
+def test_parity_sums_bit_exact(DeviceState, n_shots):
+    rng = np.random.default_rng(n_shots)
+    samples = rng.integers(0, 2**40, size=n_shots, dtype=np.uint64)
+    masks = rng.integers(0, 2**40, size=300, dtype=np.uint64)
+    masks[0] = 0
+    ref = O.parity_sums(samples, masks)
+    with DeviceState(3) as st:
+        assert np.array_equal(st.parity_sums(samples, masks), ref)
+        vals, counts = O.frequencies_from_samples(samples % np.uint64(64))
+        ref_w = O.parity_sums(samples % np.uint64(64), masks)
+        assert np.array_equal(st.parity_sums(vals, masks, counts=counts), ref_w)
+
+
+@pytest.mark.parametrize("bits", [3, 14, 30])
+def test_frequencies_bit_exact(DeviceState, bits):
+    rng = np.random.default_rng(bits)
+    samples = rng.integers(0, 2**bits, size=50_000, dtype=np.uint64) << np.uint64(2)
+    keep = ((1 << bits) - 1) << 2
+    vals, counts = O.frequencies_from_samples(samples >> np.uint64(2))
+    with DeviceState(3) as st:
+        k, c = st.frequencies(samples, keep)
+        assert np.array_equal(k, vals) and np.array_equal(c, counts)
+
+
+@pytest.mark.parametrize("n", [3, 7, 13, 16])
+def test_sampling_inverse_cdf_matches_oracle(DeviceState, n):
+    """Same Philox uniforms + same probabilities => same indices (except shots that land within rounding of a
+    bin edge), in Z, X and Y bases."""
+    psi = random_state(n, 5 * n)
+    rng = np.random.default_rng(n)
+    xb = int(rng.integers(0, 2**n))
+    yb = int(rng.integers(0, 2**n)) & ~xb
+    basis = {n - 1 - b: ("X" if (xb >> b) & 1 else "Y") for b in range(n) if ((xb | yb) >> b) & 1}
+    rot = O.run_gates(n, O.measurement_basis_gates(basis), psi)
+    p = np.abs(rot) ** 2
+    cdf = np.cumsum(p)
+    n_shots, seed = 20_000, 1234 + n
+    u = O.philox_uniform53(n_shots, seed)
+    target = u * cdf[-1]
+    ref_idx = np.searchsorted(cdf, target, side="right")
+    with DeviceState(n) as st:
+        st.from_numpy(psi)
+        got, total = st.sample(xb, yb, n_shots, seed, return_total=True)
+        assert abs(total - 1.0) < 1e-12
+        assert np.array_equal(st.to_numpy(), psi)  # psi untouched
+        edge = np.minimum(np.abs(cdf[np.minimum(ref_idx, 2**n - 1)] - target), np.abs(cdf[np.maximum(ref_idx - 1, 0)] - target))
+        mismatch = got != ref_idx.astype(np.uint64)
+        assert np.all(edge[mismatch] < 1e-12)
+        assert mismatch.mean() < 1e-3
+        # device-resident samples feed K3 without a host round trip
+        dev = st.sample(xb, yb, n_shots, seed, on_device=True)
+        masks = rng.integers(0, 2**n, size=17, dtype=np.uint64)
+        assert np.array_equal(st.parity_sums(dev, masks), O.parity_sums(got, masks))
+
+
+@pytest.mark.parametrize("bit", [0, 3, 7, 9])
+def test_global_local_bit_swap_pair(DeviceState, bit):
+    """K4 on one GPU: two shards of an (n+1)-qubit state, swap the global bit with local bit `bit`."""
+    n = 10
+    full = random_state(n + 1, 99)
+    with DeviceState(n) as lo, DeviceState(n) as hi:
+        lo.from_numpy(full[: 2**n])
+        hi.from_numpy(full[2**n :])
+        lo.swap_local_pair(hi, bit)
+        idx = np.arange(2 ** (n + 1))
+        g = (idx >> n) & 1
+        l = (idx >> bit) & 1
+        src = (idx & ~((1 << n) | (1 << bit))) | (l << n) | (g << bit)
+        ref = full[src]
+        got = np.concatenate([lo.to_numpy(), hi.to_numpy()])
+        assert np.array_equal(got, ref)
+        # the two-rank form (each side moves half of the pairs) composes to the same permutation
+        lo.from_numpy(full[: 2**n])
+        hi.from_numpy(full[2**n :])
+        lo.swap_with_peer(hi.device_ptr, bit, 0, 0)
+        hi.swap_with_peer(lo.device_ptr, bit, 1, 1)
+        lo.synchronize(), hi.synchronize()
+        got = np.concatenate([lo.to_numpy(), hi.to_numpy()])
+        assert np.array_equal(got, ref)
