@@ -8,3 +8,10 @@ hand-written CUDA kernels (sm_100a) reached through the C ABI of ``include/qiboc
 """
 
 __version__ = "0.1.0"
+
+from qibochem_b200 import gates  # noqa: E402
+from qibochem_b200.circuit import Circuit  # noqa: E402
+from qibochem_b200.hamiltonian import SymbolicHamiltonian  # noqa: E402
+from qibochem_b200 import pauli as symbols  # noqa: E402  (symbols.X / symbols.Y / symbols.Z / symbols.I)
+
+__all__ = ["Circuit", "SymbolicHamiltonian", "gates", "symbols"]

@@ -1,0 +1,130 @@
+"""
+Expectation values of a Hamiltonian for a circuit: exact (state vector, K2) and from samples (K5 + K3).
+
+Reference: ``src/qibochem/measurement/result.py`` -- ``_constant_term`` :24-35,
+``_pauli_term_measurement_expectation`` :38-54, ``expectation_from_samples`` :57-118 -- plus the qibo methods they
+call.  Differences in mechanism (not in result): the reference re-simulates the whole circuit once per measurement
+group (:106-113) and reduces Counter dictionaries in Python; here the state is prepared once, each group is a
+basis-change + sampling pass on the device, and the per-term statistics are exact integer parity sums.
+"""
+
+from __future__ import annotations
+
+from collections import Counter
+
+import numpy as np
+
+from qibochem_b200.measurement.optimization import _measurement_basis_rotations
+from qibochem_b200.measurement.shot_allocation import allocate_shots
+from qibochem_b200.pauli import PauliSum
+from qibochem_b200.runtime import get_runtime
+
+
+def expectation(circuit, hamiltonian) -> float:
+    """Exact ``<psi|H|psi>`` with ``psi = circuit|0...0>`` (the function spelling of ``hamiltonian.expectation(circuit)``)."""
+    return hamiltonian.expectation(circuit)
+
+
+def _constant_term(hamiltonian) -> float:
+    """Identity coefficient of the Hamiltonian (result.py:24-35)."""
+    return hamiltonian.constant
+
+
+def _frequencies_to_arrays(frequencies):
+    """Counter {"0110": 5, ...} -> (keys as integers read MSB-first, counts, total shots)."""
+    keys = np.array([int(k, 2) if isinstance(k, str) else int(k) for k in frequencies.keys()], dtype=np.uint64)
+    counts = np.array(list(frequencies.values()), dtype=np.int64)
+    return keys, counts, int(counts.sum())
+
+
+def _z_terms_from_frequencies(keys: np.ndarray, counts: np.ndarray, masks: np.ndarray) -> np.ndarray:
+    """Exact integer sums  S_j = sum_keys count * (-1)^{popcount(key & mask_j)}  on the device (K3)."""
+    if keys.size == 0 or masks.size == 0:
+        return np.zeros(masks.size, dtype=np.int64)
+    st = get_runtime().state(1)  # K3 only needs a device context
+    return st.parity_sums(keys, masks, counts=counts)
+
+
+def _pauli_term_measurement_expectation(expression: PauliSum, frequencies: Counter, qubit_map) -> float:
+    """Expectation of an expression of Pauli terms from frequencies measured in the terms' own bases: X/Y are read
+    as Z (result.py:46); character k of a key is the outcome of qubit ``qubit_map[k]``
+    (goldens: ``tests/test_expectation_samples.py:22-26`` of the reference)."""
+    qubit_map = list(qubit_map)
+    keys, counts, total = _frequencies_to_arrays(frequencies)
+    if total == 0:
+        return 0.0
+    nchar = len(next(iter(frequencies)))
+    coeffs, masks = [], []
+    const = 0.0
+    for (x, z), c in expression.terms.items():
+        support = x | z
+        if support == 0:
+            const += complex(c).real
+            continue
+        m = 0
+        q = 0
+        while support >> q:
+            if (support >> q) & 1:
+                m |= 1 << (nchar - 1 - qubit_map.index(q))
+            q += 1
+        coeffs.append(complex(c).real)
+        masks.append(m)
+    sums = _z_terms_from_frequencies(keys, counts, np.array(masks, dtype=np.uint64))
+    return float(const + np.dot(np.array(coeffs), sums / total))
+
+
+def expectation_from_samples(
+    circuit,
+    hamiltonian,
+    n_shots: int = 1000,
+    grouping: str | None = None,
+    n_shots_per_pauli_term: bool = True,
+    shot_allocation: list[int] | None = None,
+    seed: int | None = None,
+) -> float:
+    """Expectation value of ``hamiltonian`` from sample measurements of ``circuit``.
+
+    Args:
+        circuit: ansatz circuit
+        hamiltonian: ``SymbolicHamiltonian``
+        n_shots: shots per group of terms (or the total budget if ``n_shots_per_pauli_term`` is False)
+        grouping: ``None`` (every term measured separately) or ``"qwc"``
+        n_shots_per_pauli_term: use ``n_shots`` for every group
+        shot_allocation: shots per group when ``n_shots_per_pauli_term`` is False
+        seed: Philox key of the device sampler (extra to the reference's signature; default: fresh entropy)
+    """
+    from qibochem_b200.circuit import _next_seed
+
+    grouped_terms = _measurement_basis_rotations(hamiltonian, grouping=grouping)
+    if not n_shots_per_pauli_term:
+        if shot_allocation is None:
+            shot_allocation = allocate_shots(grouped_terms, n_shots)
+        if len(shot_allocation) != len(grouped_terms):
+            raise ValueError(f"{len(shot_allocation) = } doesn't match the number of grouped terms ({len(grouped_terms)})!")
+
+    total = _constant_term(hamiltonian)
+    if not grouped_terms:
+        return total
+    n = circuit.nqubits
+    state = circuit.run_on_device()  # psi is prepared ONCE; the reference re-runs the circuit per group
+    base_seed = _next_seed() if seed is None else int(seed)
+    for i, (expression, measurement_gates, _rotation_gates) in enumerate(grouped_terms):
+        nshots = n_shots if n_shots_per_pauli_term else int(shot_allocation[i])
+        if not nshots:
+            continue
+        xb = sum(1 << (n - 1 - g.qubits[0]) for g in measurement_gates if g.basis[0] == "X")
+        yb = sum(1 << (n - 1 - g.qubits[0]) for g in measurement_gates if g.basis[0] == "Y")
+        samples = state.sample(xb, yb, nshots, (base_seed + 0x9E3779B97F4A7C15 * (i + 1)) % (1 << 64), on_device=True)
+        coeffs, masks = [], []
+        for (x, z), c in expression.terms.items():
+            support = x | z
+            m, q = 0, 0
+            while support >> q:
+                if (support >> q) & 1:
+                    m |= 1 << (n - 1 - q)
+                q += 1
+            coeffs.append(complex(c).real)
+            masks.append(m)
+        sums = state.parity_sums(samples, np.array(masks, dtype=np.uint64))
+        total += float(np.dot(np.array(coeffs), sums / nshots))
+    return total

@@ -61,3 +61,43 @@ def masks_from_terms(n, terms):
 
 def term_list(terms):
     return [(c, list(k)) for k, c in terms.items() if k]
+
+
+def h2_molecule():
+    """H2 / STO-3G at 0.74804 Angstrom from the integrals printed at doc/source/tutorials/hamiltonian.rst:40
+    (fermionic Hamiltonian: h_pp and V_pqrs = tei[p,q,r,s] / 2); MP2 denominators need orbital energies, which the
+    docs do not print -- eps is a placeholder and only used where stated."""
+    import numpy as np
+
+    from qibochem_b200.driver import Molecule
+
+    oei = np.diag([-1.248461959132892, -0.48007161818330846])
+    tei = np.zeros((2, 2, 2, 2))
+    v = {
+        (0, 0, 0, 0): 0.3366109237586995, (0, 0, 1, 1): 0.09083064962340165, (0, 1, 0, 1): 0.09083064962340165,
+        (0, 1, 1, 0): 0.33115823068165495, (1, 0, 0, 1): 0.3311582306816552, (1, 0, 1, 0): 0.09083064962340165,
+        (1, 1, 0, 0): 0.09083064962340165, (1, 1, 1, 1): 0.348087115228365,
+    }  # fmt: skip
+    for k, val in v.items():
+        tei[k] = 2 * val
+    return Molecule.from_integrals(oei, tei, nelec=2, e_nuc=0.7074183344740923, eps=np.array([-0.58, 0.67]))
+
+
+def synthetic_molecule(n_spatial: int, nelec: int, seed: int, scale: float = 0.1):
+    """Molecule-shaped synthetic integrals: symmetric h_pq and g_pqrs with the 8-fold
+    permutational symmetry of real orbitals, N(0, scale^2), seeded; plus a diagonal one-body ladder so that the HF
+    determinant is a sensible reference.  NOT a real molecule (PySCF is unavailable): labelled '<X>-shaped'."""
+    import numpy as np
+
+    from qibochem_b200.driver import Molecule
+
+    rng = np.random.default_rng(seed)
+    h = rng.normal(scale=scale, size=(n_spatial, n_spatial))
+    h = 0.5 * (h + h.T) + np.diag(np.linspace(-1.5, 0.5, n_spatial))
+    g = rng.normal(scale=scale, size=(n_spatial,) * 4)  # chemist notation (pq|rs)
+    g = g + g.transpose(1, 0, 2, 3)
+    g = g + g.transpose(0, 1, 3, 2)
+    g = g + g.transpose(2, 3, 0, 1)
+    g = g / 8.0
+    tei = np.einsum("pqrs->prsq", g)  # second-quantisation order used by the reference (molecule.py:190-195)
+    return Molecule.from_integrals(h, tei, nelec=nelec, e_nuc=0.3, eps=np.diag(h).copy())

@@ -105,6 +105,15 @@ def main():
         progs[s] = [[g.name + ("_dagger" if g.dag else ""), list(g.qubits), list(g.params)] for g in circ.queue]
     json.dump(progs, open(f"{OUT}/expi_pauli_programs.json", "w"), indent=0)
 
+    # ---- BK image of the HF occupation vector (ansatz.py:276-281 with _ansatz._bk_matrix)
+    import numpy as _np
+
+    bk = {}
+    for n, ne in [(4, 2), (6, 2), (7, 3), (8, 4), (12, 4), (13, 7), (16, 9)]:
+        occ = _np.concatenate((_np.ones(ne, dtype=_np.int8), _np.zeros(n - ne, dtype=_np.int8)))
+        bk[f"{n}_{ne}"] = [int(v) for v in (_ansatz._bk_matrix(n) @ occ) % 2]
+    json.dump(bk, open(f"{OUT}/bk_occupation.json", "w"))
+
     # ---- QWC / general commuting groups (measurement/util.py:22-79), deterministic given the node order
     import numpy as np
 

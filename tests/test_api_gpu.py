@@ -1,0 +1,304 @@
+"""GPU tests of the qibochem-facing API; they mirror the reference's own tests of the hot path
+(tests/test_ansatz.py, tests/test_expectation_samples.py) with the CPU oracle standing in for qibo."""
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from tests import fixtures as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _lib(native_lib):
+    return native_lib
+
+
+def _api():
+    import qibochem_b200 as qb
+    from qibochem_b200 import Circuit, SymbolicHamiltonian, gates
+    from qibochem_b200.ansatz import circuit_ansatz, hf_circuit, ucc_circuit
+    from qibochem_b200.ansatz.ansatz import _expi_pauli
+    from qibochem_b200.measurement import expectation, expectation_from_samples
+    from qibochem_b200.measurement.result import _pauli_term_measurement_expectation
+    from qibochem_b200.pauli import X, Y, Z
+
+    return locals()
+
+
+def gate_list_of(circuit):
+    """qibochem_b200 gate queue -> oracle gate list."""
+    name = {"x": "X", "y": "Y", "z": "Z", "h": "H", "s": "S", "sdg": "SDG", "cx": "CNOT", "cz": "CZ", "rx": "RX", "ry": "RY", "rz": "RZ"}
+    out = []
+    for g in circuit.queue:
+        if g.name == "pauli_rotation":
+            out += O.expi_pauli_gates(g.pauli_string, -0.5 * complex(g.parameters[0]).real)
+        elif g.name != "measure":
+            out.append((name[g.name], g.qubits, g.parameters[0] if g.parameters else None))
+    return out
+
+
+def doc_circuit(A, n, f=0.1):
+    g = A["gates"]
+    c = A["Circuit"](n)
+    c.add(g.RX(i, f) for i in range(n))
+    c.add(g.RZ(i, f) for i in range(n))
+    c.add(g.CNOT(i, i + 1) for i in range(n - 1))
+    c.add(g.RX(i, 2 * f) for i in range(n))
+    c.add(g.RZ(i, 2 * f) for i in range(n))
+    return c
+
+
+def test_hf_circuit_energy_jw_and_bk():
+    """tests/test_ansatz.py:115-134 analogue on the doc fixture geometry (ansatz.rst:73)."""
+    A = _api()
+    mol = F.h2_molecule()
+    for mapping in (None, "bk"):
+        ham = mol.hamiltonian(ferm_qubit_map=mapping)
+        circuit = A["hf_circuit"](mol.nso, mol.nelec, ferm_qubit_map=mapping)
+        assert ham.expectation(circuit) == pytest.approx(F.H2_HF_ENERGY, abs=1e-12)
+    assert A["expectation"](A["hf_circuit"](4, 2), mol.hamiltonian()) == pytest.approx(F.H2_HF_ENERGY, abs=1e-12)
+    assert mol.hamiltonian().expectation(A["Circuit"](4)) == pytest.approx(F.H2_VACUUM_ENERGY, abs=1e-12)
+
+
+@pytest.mark.parametrize("pauli_string", ["Z1", "Z0 Z1", "X0 X1", "Y0 Y1"])
+def test_expi_pauli(pauli_string):
+    """tests/test_ansatz.py:137-164: state of _expi_pauli(theta) == exp(i theta P)|00> (oracle gate program)."""
+    A = _api()
+    theta = 0.4321
+    got = A["_expi_pauli"](2, pauli_string, theta)().state()
+    ref = O.run_gates(2, O.expi_pauli_gates(pauli_string, theta))
+    assert np.abs(got - ref).max() < 1e-12
+
+
+@pytest.mark.parametrize("excitation,mapping", [([0, 2], None), ([0, 1, 2, 3], None), ([0, 2], "bk")])
+def test_ucc_circuit(excitation, mapping):
+    """tests/test_ansatz.py:167-217, but from the HF state (the reference's vacuum start is degenerate)."""
+    A = _api()
+    theta, n = 0.1, 4
+    kw = {} if mapping is None else {"ferm_qubit_map": mapping}
+    circuit = A["hf_circuit"](n, 2, **kw) + A["ucc_circuit"](n, excitation, theta=theta, **kw)
+    got = circuit().state()
+    ref = O.run_gates(n, gate_list_of(circuit))
+    assert np.abs(got - ref).max() < 1e-12
+    if mapping is None:
+        ref2 = O.run_gates(n, O.hf_gates(n, 2) + O.ucc_gates(excitation, theta))
+        assert np.abs(got - ref2).max() < 1e-12
+
+
+def test_general_gate_circuit_state_and_expectation():
+    """doc/source/tutorials/measurement.rst:155-208 and :290-325 through the public API."""
+    A = _api()
+    X, Y, Z, SH = A["X"], A["Y"], A["Z"], A["SymbolicHamiltonian"]
+    c3 = doc_circuit(A, 3)
+    ref = O.run_gates(3, gate_list_of(c3))
+    assert np.abs(c3().state() - ref).max() < 1e-12
+    assert SH(X(0) * Z(2), nqubits=3).expectation(c3) == pytest.approx(0.02847, abs=5e-6)
+    assert SH(Y(1) * Z(2), nqubits=3).expectation(c3) == pytest.approx(-0.19465, abs=5e-6)
+    bk = SH(-0.4584 + 0.3593 * Z(0) - 0.4826 * Z(1) + 0.5818 * Z(0) * Z(1) + 0.0896 * X(0) * X(1) + 0.0896 * Y(0) * Y(1))
+    assert bk.expectation(doc_circuit(A, 2)) == pytest.approx(-0.0171209, abs=5e-8)
+    assert bk.expectation(doc_circuit(A, 2)) == pytest.approx(
+        O.expectation_terms_gatepath(O.run_gates(2, F.doc_circuit_gates(2)), 2, F.BK_H2_TERMS, F.BK_H2_CONST), abs=1e-12
+    )
+
+
+def test_vqe_energy_callable_reaches_fci():
+    """README.md:25-48 / adaptive.rst:95-106: minimise E(params) over the 8 RZ angles of HF+UCCD with scipy."""
+    from scipy.optimize import minimize
+
+    A = _api()
+    mol = F.h2_molecule()
+    ham = mol.hamiltonian()
+    circuit = A["hf_circuit"](4, 2) + A["ucc_circuit"](4, [0, 1, 2, 3])
+
+    def energy(params):
+        circuit.set_parameters(params)
+        return ham.expectation(circuit)
+
+    res = minimize(energy, np.zeros(8), method="BFGS")
+    assert res.fun == pytest.approx(F.H2_FCI_ENERGY, abs=1e-8)
+
+
+@pytest.mark.parametrize("n_spatial,nelec,seed", [(4, 4, 1), (6, 4, 2)])
+def test_uccsd_energy_molecule_shaped(n_spatial, nelec, seed):
+    """C2-like configuration (LiH-shaped: 12 qubits, 4 electrons, 92 excitations / 640 rotations): circuit_ansatz +
+    exact expectation vs the oracle's gate-by-gate path (reference gate program + per-term expectation)."""
+    A = _api()
+    mol = F.synthetic_molecule(n_spatial, nelec, seed)
+    n = mol.nso
+    ham = mol.hamiltonian()
+    rng = np.random.default_rng(seed)
+    from qibochem_b200.ansatz import generate_excitations
+
+    exc = []
+    for order in (2, 1):
+        exc += generate_excitations(order, range(nelec), range(nelec, n))
+    thetas = rng.uniform(-0.1, 0.1, size=len(exc))
+    circuit = A["circuit_ansatz"](mol, "ucc", excitations=exc, thetas=thetas)
+    e = ham.expectation(circuit)
+    gates_ref = O.hf_gates(n, nelec)
+    for ex, th in zip(exc, thetas):
+        gates_ref += O.ucc_gates(ex, th)
+    psi = O.run_gates(n, gates_ref)
+    assert np.abs(circuit().state() - psi).max() < 1e-12
+    x, z, c = ham.index_masks()
+    assert e == pytest.approx(O.expectation_masks(psi, x, z, c, ham.constant), abs=1e-10)
+    if n <= 8:
+        assert e == pytest.approx(O.expectation_terms_gatepath(psi, n, ham.terms, ham.constant), abs=1e-10)
+
+
+@pytest.mark.parametrize(
+    "term,frequencies,qubit_map,expected",
+    [
+        ("X0", {"10": 5}, [0, 1], -1.0),
+        ("X2", {"010": 5}, [0, 2, 5], -1.0),
+        ("Y4", {"110": 5}, [0, 2, 4], 1.0),
+        ("X0 Y1", {"11": 5}, [0, 1], 1.0),
+        ("X0 Y1 + X0", {"11": 5}, [0, 1], 0.0),
+    ],
+)
+def test_pauli_term_measurement_expectation(term, frequencies, qubit_map, expected):
+    """tests/test_expectation_samples.py:19-31 -- exact goldens."""
+    A = _api()
+    from qibochem_b200.pauli import PauliSum
+
+    expr = PauliSum()
+    for t in term.split(" + "):
+        expr = expr + PauliSum.from_string(t)
+    assert A["_pauli_term_measurement_expectation"](expr, frequencies, qubit_map) == expected
+
+
+def test_z_hamiltonian_expectation_from_samples_method():
+    A = _api()
+    Z, SH = A["Z"], A["SymbolicHamiltonian"]
+    ham = SH(0.5 * Z(0) * Z(2) - 2.0 * Z(1) + 0.25, nqubits=3)
+    freq = {"000": 3, "101": 2, "011": 5}
+    ref = 0.25 + 0.5 * O.z_expectation_from_frequencies(freq, [0, 1, 2], [0, 2]) - 2.0 * O.z_expectation_from_frequencies(freq, [0, 1, 2], [1])
+    assert ham.expectation_from_samples(freq) == pytest.approx(ref, abs=1e-15)
+    # qubit_map permutes which character belongs to which qubit
+    ref2 = 0.25 + 0.5 * O.z_expectation_from_frequencies(freq, [2, 0, 1], [0, 2]) - 2.0 * O.z_expectation_from_frequencies(freq, [2, 0, 1], [1])
+    assert ham.expectation_from_samples(freq, qubit_map=[2, 0, 1]) == pytest.approx(ref2, abs=1e-15)
+
+
+def test_expectation_from_samples_deterministic_states():
+    """tests/test_expectation_samples.py:34-47."""
+    A = _api()
+    g, SH, X, Z = A["gates"], A["SymbolicHamiltonian"], A["X"], A["Z"]
+    for terms, to_add in ((Z(0), [g.X(0)]), (Z(0) * Z(1), [g.X(0)]), (X(0), [g.H(0)])):
+        ham = SH(terms, nqubits=2)
+        c = A["Circuit"](2)
+        c.add(to_add)
+        assert A["expectation_from_samples"](c, ham) == pytest.approx(ham.expectation(c))
+
+
+def test_expectation_manual_and_invalid_shot_allocation():
+    """tests/test_expectation_samples.py:57-82."""
+    A = _api()
+    g, SH, X, Z = A["gates"], A["SymbolicHamiltonian"], A["X"], A["Z"]
+    ham = SH(X(0) + Z(0))
+    for to_add, alloc, expected in (([g.H(0)], [10, 0], 1.0), ([g.X(0), g.Z(0)], [0, 10], -1.0)):
+        c = A["Circuit"](1)
+        c.add(to_add)
+        assert A["expectation_from_samples"](c, ham, n_shots_per_pauli_term=False, shot_allocation=alloc) == pytest.approx(expected)
+    with pytest.raises(ValueError):
+        A["expectation_from_samples"](A["Circuit"](1), SH(Z(0) + X(0)), n_shots_per_pauli_term=False, shot_allocation=(1,))
+
+
+def test_measurement_grouping_functionality():
+    """tests/test_expectation_samples.py:84-112: sampled == exact within abs 0.08 at 10^4 shots, None and qwc."""
+    A = _api()
+    g, SH, X, Y, Z = A["gates"], A["SymbolicHamiltonian"], A["X"], A["Y"], A["Z"]
+    hams = [
+        SH(Z(2)),
+        SH(0.2 * X(0) + Y(2) + 13.0),
+        SH(Z(0) + X(0) * Y(1) + Z(0) * Y(2)),
+        SH(Y(0) + Z(1) + X(0) * Z(2)),
+        SH(0.1 * X(0) * X(1) * Y(2) + 0.2 * X(0) * Y(1) * Y(2) + 0.3 * Y(0) * X(1) * X(2) - 3.14 * Y(0) * Y(1) * X(2)),
+    ]
+    n = 3
+    c = A["Circuit"](n)
+    c.add(g.RX(i, 0.1 * i) for i in range(n))
+    c.add(g.CNOT(i, i + 1) for i in range(n - 1))
+    c.add(g.RZ(i, 0.2 * i) for i in range(n))
+    for ham in hams:
+        exact = ham.expectation(c)
+        assert exact == pytest.approx(O.expectation_terms_gatepath(O.run_gates(n, gate_list_of(c)), n, ham.terms, ham.constant), abs=1e-12)
+        for grouping in (None, "qwc"):
+            assert A["expectation_from_samples"](c, ham, n_shots=10000, grouping=grouping) == pytest.approx(exact, abs=0.08)
+        with pytest.raises(NotImplementedError):
+            A["expectation_from_samples"](c, ham, grouping="gc")
+
+
+def test_h2_hf_energy_from_samples():
+    """tests/test_expectation_samples.py:115-136 (qwc instead of gc): abs 0.01 at 5*10^4 shots, both shot modes."""
+    A = _api()
+    ham = F.h2_molecule().hamiltonian()
+    c = A["Circuit"](4)
+    c.add(A["gates"].X(i) for i in range(2))
+    for per_term in (True, False):
+        e = A["expectation_from_samples"](c, ham, n_shots_per_pauli_term=per_term, n_shots=50000, grouping="qwc")
+        assert e == pytest.approx(ham.expectation(c), abs=0.01)
+
+
+def test_sampled_energy_matches_reference_arithmetic_on_identical_samples():
+    """C3-like check (BeH2-shaped, 14 qubits, QWC groups): the same device samples pushed through the oracle's
+    restatement of qibo's frequency arithmetic give the same group energies; integer sums are bit-exact."""
+    A = _api()
+    from qibochem_b200.measurement.optimization import _measurement_basis_rotations
+    from qibochem_b200.runtime import get_runtime
+
+    mol = F.synthetic_molecule(7, 6, 3)
+    n = mol.nso
+    ham = mol.hamiltonian()
+    groups = _measurement_basis_rotations(ham, "qwc")
+    assert 1 < len(groups) < ham.nterms
+    circuit = A["hf_circuit"](n, 6) + A["ucc_circuit"](n, [0, 1, 6, 7], 0.3) + A["ucc_circuit"](n, [2, 9], -0.2)
+    st = circuit.run_on_device()
+    assert st is get_runtime()._states[n]
+    nshots = 20000
+    for gi, (expr, m_gates, _) in enumerate(groups[:6]):
+        xb = sum(1 << (n - 1 - g.qubits[0]) for g in m_gates if g.basis[0] == "X")
+        yb = sum(1 << (n - 1 - g.qubits[0]) for g in m_gates if g.basis[0] == "Y")
+        samples = st.sample(xb, yb, nshots, 77 + gi)
+        qubit_map = [g.qubits[0] for g in m_gates]
+        # frequencies over the measured qubits, in gate order, as qibo would report them
+        bits = np.stack([(samples >> np.uint64(n - 1 - q)) & np.uint64(1) for q in qubit_map], axis=1)
+        keys = ["".join(map(str, row)) for row in bits.astype(int)]
+        from collections import Counter
+
+        freq = Counter(keys)
+        ref = 0.0
+        masks, coeffs = [], []
+        for (x, z), c in expr.terms.items():
+            qs = [q for q in range(n) if ((x | z) >> q) & 1]
+            ref += O.z_expectation_from_frequencies(freq, qubit_map, qs, complex(c).real)
+            masks.append(sum(1 << (n - 1 - q) for q in qs))
+            coeffs.append(complex(c).real)
+        sums = st.parity_sums(samples, masks)
+        assert np.array_equal(sums, O.parity_sums(samples, masks))
+        got = float(np.dot(coeffs, sums / nshots))
+        assert got == pytest.approx(ref, abs=1e-12)
+        assert A["_pauli_term_measurement_expectation"](expr, freq, qubit_map) == pytest.approx(ref, abs=1e-12)
+
+
+def test_result_frequencies_protocol():
+    """circuit(nshots=) -> frequencies(binary=True): character k <-> k-th measured qubit (result.py:113-116)."""
+    A = _api()
+    g = A["gates"]
+    c = A["Circuit"](4)
+    c.add([g.X(0), g.X(3)])
+    c.add(g.M(3))
+    c.add(g.M(1))
+    c.add(g.M(0, basis="Z"))
+    freq = c(nshots=100).frequencies(binary=True)
+    assert dict(freq) == {"101": 100}
+    c = A["Circuit"](2)
+    c.add(g.H(0))
+    c.add(g.M(0, basis=g.X))  # measured in the X basis: |+> always gives 0
+    c.add(g.M(1))
+    assert dict(c(nshots=64).frequencies()) == {"00": 64}
+    c = A["Circuit"](1)
+    c.add([g.H(0), g.S(0)])  # |+i>
+    c.add(g.M(0, basis=g.Y))
+    assert dict(c(nshots=50).frequencies()) == {"0": 50}

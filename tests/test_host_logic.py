@@ -1,0 +1,264 @@
+"""CPU tests of the host side: circuit lowering, parameter protocol, fermion maps, excitation order, grouping,
+shot allocation -- against the oracle and the golden fixtures generated from the reference's own modules."""
+
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from qibochem_b200 import Circuit, SymbolicHamiltonian, gates
+from qibochem_b200.ansatz import circuit_ansatz, generate_excitations, hf_circuit, mp2_amplitude, ucc_circuit
+from qibochem_b200.ansatz._fermion import bk_ladder, bk_occupation_mask, excitation_generator
+from qibochem_b200.ansatz.utils import _sort_excitations
+from qibochem_b200.measurement.optimization import (
+    _check_terms_commutativity,
+    _group_commuting_terms,
+    _measurement_basis_rotations,
+)
+from qibochem_b200.measurement.shot_allocation import allocate_shots, allocate_shots_by_variance
+from qibochem_b200.pauli import PauliSum, X, Y, Z
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def run_program_with_oracle(circuit, initial=None):
+    """Execute a compiled Pauli-rotation program with the oracle's mask arithmetic (host-logic check only)."""
+    prog = circuit.program()
+    n = circuit.nqubits
+    if initial is None:
+        psi = np.zeros(2**n, dtype=complex)
+        psi[prog.basis_index] = 1.0
+    else:
+        psi = initial[np.arange(2**n) ^ prog.basis_index]
+    for x, z, a in zip(prog.xmask.tolist(), prog.zmask.tolist(), prog.angle.tolist()):
+        psi = O.apply_pauli_rotation(psi, x, z, a)
+    return psi * prog.phase
+
+
+ORACLE_NAME = {"x": "X", "y": "Y", "z": "Z", "h": "H", "s": "S", "sdg": "SDG", "cx": "CNOT", "cz": "CZ", "swap": "SWAP",
+               "rx": "RX", "ry": "RY", "rz": "RZ"}  # fmt: skip
+
+
+def test_gate_lowering_reproduces_gate_matrices_including_global_phase():
+    n = 4
+    rng = np.random.default_rng(0)
+    psi0 = rng.normal(size=2**n) + 1j * rng.normal(size=2**n)
+    psi0 /= np.linalg.norm(psi0)
+    queue = [gates.H(0), gates.X(1), gates.CNOT(0, 2), gates.S(2), gates.RX(1, 0.3), gates.CZ(1, 3), gates.SDG(0),
+             gates.Y(3), gates.RY(2, -0.7), gates.SWAP(0, 3), gates.Z(1), gates.RZ(3, 1.1), gates.CNOT(3, 1), gates.H(2)]  # fmt: skip
+    c = Circuit(n)
+    c.add(queue)
+    ref = psi0.copy()
+    for g in queue:
+        ref = O.apply_gate(ref, n, O.gate_matrix(ORACLE_NAME[g.name], g.parameters[0] if g.parameters else None), g.qubits)
+    got = run_program_with_oracle(c, psi0)
+    assert np.abs(got - ref).max() < 1e-13
+
+
+def test_leading_x_gates_become_the_initial_basis_state():
+    c = hf_circuit(6, 2)
+    prog = c.program()
+    assert prog.basis_index == 0b110000 and prog.xmask.size == 0
+    c.add(gates.H(0))
+    c.add(gates.X(5))  # not leading any more: lowered to a rotation
+    assert c.program().basis_index == 0b110000 and c.program().xmask.size == 4
+
+
+@pytest.mark.parametrize("excitation", [[0, 1, 2, 3], [0, 2], [1, 3, 4, 6], [0, 5], [2, 3, 4, 5]])
+def test_ucc_circuit_equals_reference_gate_program(excitation):
+    """mask program of ucc_circuit == the reference's gate-by-gate program (oracle restatement of _expi_pauli)."""
+    n, ne, theta = 7, 4, 0.2371
+    c = hf_circuit(n, ne) + ucc_circuit(n, excitation, theta)
+    ref = O.run_gates(n, O.hf_gates(n, ne) + O.ucc_gates(excitation, theta))
+    assert np.abs(run_program_with_oracle(c) - ref).max() < 1e-13
+    c2 = hf_circuit(n, ne) + ucc_circuit(n, excitation, theta, trotter_steps=3)
+    ref2 = O.run_gates(n, O.hf_gates(n, ne) + O.ucc_gates(excitation, theta, trotter_steps=3))
+    assert np.abs(run_program_with_oracle(c2) - ref2).max() < 1e-13
+
+
+def test_ucc_parameters_follow_reference_convention():
+    """examples/ucc_example1.py:17 -- RZ multipliers per string; values are complex-typed with zero imaginary part."""
+    theta = 0.1
+    params = [p for (p,) in ucc_circuit(4, [0, 1, 2, 3], theta).get_parameters()]
+    assert [p.real / theta for p in params] == pytest.approx([-0.25, 0.25, 0.25, 0.25, -0.25, -0.25, -0.25, 0.25])
+    assert all(isinstance(p, complex) and p.imag == 0 for p in params)
+    params = [p for (p,) in ucc_circuit(4, [0, 2], theta).get_parameters()]
+    assert [p.real / theta for p in params] == pytest.approx([-1.0, 1.0])
+    strings = [g.pauli_string for g in ucc_circuit(4, [0, 1, 2, 3]).queue]
+    assert strings[0] == "X0 X1 Y2 X3" and strings[-1] == "Y0 Y1 X2 Y3"  # tests/test_ansatz.py:175-184
+    assert [g.pauli_string for g in ucc_circuit(4, [0, 2], ferm_qubit_map="bk").queue] == ["X0 Y1 X2", "Y0 Y1 Y2"]
+
+
+def test_set_parameters_updates_compiled_program():
+    c = hf_circuit(4, 2) + ucc_circuit(4, [0, 1, 2, 3], 0.1)
+    c.add(gates.RX(0, 0.5))
+    prog = c.program()
+    new = np.linspace(0.1, 0.9, 9)
+    c.set_parameters(new)
+    assert c.program() is prog
+    assert np.allclose(prog.angle, new)
+    assert [p for (p,) in c.get_parameters()] == pytest.approx(list(new))
+    with pytest.raises(ValueError):
+        c.set_parameters([0.1])
+    d = c.copy()
+    d.add(gates.RZ(1, 0.2))
+    assert len(d.get_parameters()) == 10 and len(c.get_parameters()) == 9
+
+
+def test_ansatz_argument_checks():
+    """tests/test_ansatz.py:612-638 of the reference (the parts on the hot path)."""
+    for fn in (hf_circuit, ucc_circuit):
+        with pytest.raises(NotImplementedError):
+            fn(2, [0, 1], ferm_qubit_map="zc")
+    for excitation in ([], [1000]):
+        with pytest.raises(ValueError):
+            ucc_circuit(2, excitation)
+    with pytest.raises(ValueError):
+        ucc_circuit(2, [0, 1], trotter_steps=0)
+
+    class Mol:
+        nso, nelec, n_active_orbs, n_active_e = 4, 2, None, None
+        eps = np.array([-0.5, 0.5])
+        tei = np.zeros((2, 2, 2, 2))
+
+    with pytest.raises(ValueError):
+        circuit_ansatz(Mol(), "zc")
+    with pytest.raises(ValueError):
+        circuit_ansatz(Mol(), "ucc", excitations=[[0]])
+    with pytest.raises(ValueError):
+        circuit_ansatz(Mol(), "ucc", excitations=[[0, 1]], thetas=[0.1, 0.2])
+    c = circuit_ansatz(Mol(), "ucc")
+    assert [g.name for g in c.queue].count("pauli_rotation") == 8 + 2 + 2  # [0,1,2,3], [0,2], [1,3]
+
+
+def test_excitations_equal_reference_outputs():
+    g = json.load(open(os.path.join(GOLDEN, "excitations.json")))
+    for key, val in g["generate"].items():
+        order, n, ne = map(int, key.split("_"))
+        assert generate_excitations(order, range(ne), range(ne, n)) == val
+    assert generate_excitations(1, [0, 1], [2, 3], conserve_spin=False) == g["no_spin"]
+    assert [len(generate_excitations(o, range(14), range(14, 30))) for o in (2, 1)] == g["counts_30_14"]
+    # goldens of tests/test_ansatz.py:642-667
+    assert generate_excitations(1, [0, 1], [2, 3]) == [[0, 2], [1, 3]]
+    assert generate_excitations(2, [2, 3], [4, 5]) == [[2, 3, 4, 5]]
+    assert generate_excitations(3, [0, 1], [2, 3]) == [[]]
+    assert _sort_excitations([[0, 2], [0, 4], [1, 3], [1, 5]]) == [[0, 2], [1, 3], [0, 4], [1, 5]]
+    assert _sort_excitations([[0, 1, 2, 5], [0, 1, 2, 3], [0, 1, 3, 4], [0, 1, 4, 5]]) == [[0, 1, 2, 3], [0, 1, 4, 5], [0, 1, 2, 5], [0, 1, 3, 4]]
+    with pytest.raises(NotImplementedError):
+        _sort_excitations([[1, 2, 3, 4, 5, 6]])
+    with pytest.raises(ValueError):
+        _sort_excitations([[0, 1], [0, 1, 2, 3]])
+
+
+def test_mp2_amplitude():
+    assert mp2_amplitude([0, 2], np.random.rand(4), np.random.rand(4, 4)) == 0.0
+    with pytest.raises(ValueError):
+        mp2_amplitude([0, 1, 2], np.zeros(2), np.zeros((2, 2, 2, 2)))
+    rng = np.random.default_rng(1)
+    eps, tei = np.sort(rng.normal(size=3)), rng.normal(size=(3, 3, 3, 3))
+    # (i,j,a,b) = (0,1,4,5): spin(0)==spin(5)? no -> direct term vanishes; exchange: spin(0)==spin(4), spin(1)==spin(5)
+    t = mp2_amplitude([0, 1, 4, 5], eps, tei)
+    assert t == pytest.approx((0.0 - tei[0, 0, 2, 2]) / (2 * eps[0] - 2 * eps[2]))
+
+
+def test_jw_generator_matches_oracle_and_bk_is_canonical():
+    for ex in ([0, 1, 2, 3], [0, 2], [1, 3, 6, 9], [2, 7]):
+        mine = excitation_generator(ex).strings()
+        ref = O.ucc_pauli_terms(ex)
+        assert [s for s, _ in mine] == [s for s, _ in ref]
+        assert np.allclose([c for _, c in mine], [c for _, c in ref])
+    for n in (3, 6, 8):  # canonical anticommutation relations of the BK ladder operators
+        for p in range(n):
+            for q in range(n):
+                a, bd = bk_ladder(p, False, n), bk_ladder(q, True, n)
+                anti = (a * bd + bd * a).compress()
+                assert anti.isclose(PauliSum.identity(1.0) if p == q else PauliSum())
+    # BK image of occupation vectors == reference's _bk_matrix @ occ (mod 2), golden from the reference module
+    g = json.load(open(os.path.join(GOLDEN, "bk_occupation.json")))
+    for key, bits in g.items():
+        n, ne = map(int, key.split("_"))
+        mask = bk_occupation_mask(range(ne), n)
+        assert [(mask >> q) & 1 for q in range(n)] == bits
+
+
+def test_pauli_sum_algebra():
+    assert (X(0) * Y(0)).isclose(1j * Z(0))
+    assert (Y(1) * X(1)).isclose(-1j * Z(1))
+    assert (Z(2) * Z(2)).isclose(PauliSum.identity())
+    h = SymbolicHamiltonian(0.2 * X(0) + Y(2) + 13.0)
+    assert h.nqubits == 3 and h.constant == 13.0 and h.nterms == 2
+    x, z, c = h.index_masks()
+    assert x.tolist() == [4, 1] and z.tolist() == [0, 1] and c.tolist() == [0.2, 1.0]
+    h2 = SymbolicHamiltonian(np.float64(0.5) * Z(0) * Z(1), nqubits=4)
+    assert h2.index_masks()[1].tolist() == [0b1100]
+    big = SymbolicHamiltonian.from_index_masks(5, [3, 16], [1, 0], [0.5, -1.0], constant=2.0)
+    assert big.form.isclose(2.0 + 0.5 * X(3) * Y(4) - 1.0 * X(0))
+
+
+def test_grouping_equals_reference_outputs():
+    cases = json.load(open(os.path.join(GOLDEN, "commuting_groups.json")))
+    for case in cases:
+        t = case["terms"]
+        assert _group_commuting_terms(t, True) == case["qwc"]
+        assert _group_commuting_terms(t, False) == case["gc"]
+        for i, a in enumerate(t):
+            for j, b in enumerate(t):
+                assert _check_terms_commutativity(a, b, True) == case["commute_qwc"][i][j]
+                assert _check_terms_commutativity(a, b, False) == case["commute_gc"][i][j]
+    # tests/test_measurement_util.py:25-53 of the reference
+    assert not _check_terms_commutativity("X0 X1", "Y0 Y1", True) and _check_terms_commutativity("X0 X1", "Y0 Y1", False)
+    assert _group_commuting_terms(["X0 Z1", "X0", "Z0", "Z0 Z1"], True) == [["X0", "X0 Z1"], ["Z0", "Z0 Z1"]]
+    assert _group_commuting_terms(["X0 Y1 Z2", "X1 X2", "Z1 Y2"], False) == [["X0 Y1 Z2", "X1 X2", "Z1 Y2"]]
+
+
+def test_grouping_agrees_with_networkx_on_random_input():
+    nx = pytest.importorskip("networkx")
+    rng = np.random.default_rng(7)
+    terms = []
+    while len(terms) < 80:
+        s = " ".join(f"{'XYZ'[rng.integers(0, 3)]}{q}" for q in range(7) if rng.random() < 0.5)
+        if s and s not in terms:
+            terms.append(s)
+    for qubitwise in (True, False):
+        G = nx.Graph()
+        G.add_nodes_from(terms)
+        G.add_edges_from((a, b) for i, a in enumerate(terms) for b in terms[i + 1 :] if not _check_terms_commutativity(a, b, qubitwise))
+        col = nx.coloring.greedy_color(G)
+        ref = sorted(sorted(t for t, c in col.items() if c == k) for k in set(col.values()))
+        assert _group_commuting_terms(terms, qubitwise) == ref
+
+
+def test_measurement_groups_of_doc_example():
+    """doc/source/tutorials/measurement.rst:267 -- [['X0 X1'], ['Y0 Y1'], ['Z0', 'Z1', 'Z0 Z1']]"""
+    h = SymbolicHamiltonian(-0.4584 + 0.3593 * Z(0) - 0.4826 * Z(1) + 0.5818 * Z(0) * Z(1) + 0.0896 * X(0) * X(1) + 0.0896 * Y(0) * Y(1))
+    groups = _measurement_basis_rotations(h, "qwc")
+    assert [sorted(s for s, _ in e.strings()) for e, _, _ in groups] == [["X0 X1"], ["Y0 Y1"], ["Z0", "Z0 Z1", "Z1"]]
+    assert [[(g.qubits[0], g.basis[0]) for g in m] for _, m, _ in groups] == [[(0, "X"), (1, "X")], [(0, "Y"), (1, "Y")], [(0, "Z"), (1, "Z")]]
+    assert len(_measurement_basis_rotations(h, None)) == 5
+    with pytest.raises(NotImplementedError):
+        _measurement_basis_rotations(h, "test")
+
+
+@pytest.mark.parametrize(
+    "method,max_shots,expected",
+    [("u", None, [66, 67, 67]), (None, None, [23, 168, 9]), (None, 100, [75, 100, 25]), (None, 25, [75, 100, 25]), (None, 1000, [23, 168, 9])],
+)
+def test_allocate_shots(method, max_shots, expected):
+    """tests/test_measurement_optimisation.py:32-50 of the reference (term order X0, Z0, Y1; +-1 allowed there too)."""
+    h = SymbolicHamiltonian(5 * X(0) + 94 * Z(0) + Y(1))
+    got = allocate_shots(_measurement_basis_rotations(h), 200, method=method, max_shots_per_term=max_shots)
+    assert sum(got) == 200 and max(abs(a - b) for a, b in zip(got, expected)) <= 1
+
+
+def test_allocate_shots_edge_cases():
+    h = SymbolicHamiltonian(Z(0) + X(0))
+    assert allocate_shots(_measurement_basis_rotations(h), 1) in ([0, 1], [1, 0])
+    with pytest.raises(NameError):
+        allocate_shots(_measurement_basis_rotations(h), 1, method="wrong")
+    g = json.load(open(os.path.join(GOLDEN, "shot_allocation_variance.json")))
+    for case in g:
+        assert allocate_shots_by_variance(*case["args"]) == case["out"]
+    assert allocate_shots_by_variance(120, 20, [0.0, 16.0, 64.0], "vmsa") == [0, 20, 40]
+    assert allocate_shots_by_variance(120, 20, [0.0, 16.0, 64.0], "vpsr") == [0, 12, 24]
