@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""
+bench.py -- UCCSD energy evaluations per second on the named synthetic configuration (BASELINE.json configs[3]/[4]).
+
+One STEP = one energy evaluation of the hot path: HF basis state (K0) -> R UCCSD Pauli rotations (K1) -> expectation
+of a T-term molecular-structured Hamiltonian (K2) [-> all-reduce over shards when N > 1].
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--qubits n] [--rotations R] [--terms T]
+
+N = 1: 30 qubits (17.18 GB state >> 126 MB L2, so no L2 flush is needed between steps), R = 1024 rotations (the
+first 128 double excitations of the (30, 14) UCCSD order), T = 100 000 terms over 19 012 x-masks.
+N > 1 (launched by torchrun, one rank per GPU): weak-scaling ladder 33 q @ 2, 34 q @ 4, 35 q @ 8 (2^32 amplitudes per
+GPU), reported in 30-qubit-equivalent evaluations per second (x 2^(n-30)) so that the value is extensive.
+
+The JSON line carries the driver contract keys plus `roofline` (dominant kernel, device time from CUDA events on the
+launching stream), `cpu_baseline` (C/OpenMP port of the reference's gate-by-gate algorithm on the host cores, bounded
+sample) and `e2e` (the same step through the public Python API with host arrays in, energy out).
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "uccsd_energy_evals_per_sec"
+DEFAULT_QUBITS = {1: 30, 2: 33, 4: 34, 8: 35}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--qubits", type=int, default=None)
+    ap.add_argument("--electrons", type=int, default=None)
+    ap.add_argument("--rotations", type=int, default=1024, help="UCCSD rotation prefix (8 per double excitation)")
+    ap.add_argument("--terms", type=int, default=100_000)
+    ap.add_argument("--cpu-sample-qubits", type=int, default=24)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload(n: int, nelec: int, rotations: int, terms: int):
+    from qibochem_b200 import synthetic
+
+    rx, rz, ra, n_exc = synthetic.uccsd_rotation_stream(n, nelec, max_excitations=max(1, rotations // 8))
+    rx, rz, ra = rx[:rotations], rz[:rotations], ra[:rotations]
+    hx, hz, hc, const = synthetic.molecular_like_hamiltonian(n, terms)
+    return {"n": n, "nelec": nelec, "rx": rx, "rz": rz, "ra": ra, "hx": hx, "hz": hz, "hc": hc, "const": const,
+            "hf": synthetic.hf_index(n, nelec), "n_xmasks": int(np.unique(hx).size)}  # fmt: skip
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index: int):
+        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=self.tmp, stderr=subprocess.DEVNULL,
+            )  # fmt: skip
+        except OSError:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.tmp.flush()
+        self.tmp.seek(0)
+        sm, smax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.tmp.read().splitlines():
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])), smax.append(float(parts[1])), power.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.tmp.name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "power_w_max": float(max(power)),
+                "samples": len(sm), "reasons": sorted(reasons)}  # fmt: skip
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# CPU baseline: the reference's algorithm (gate-by-gate _expi_pauli programs + per-term expectation), C/OpenMP port
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_reference_sample(wl_full: dict, sample_qubits: int, budget_s: float = 20.0) -> dict:
+    """Times a bounded sample of the SAME workload shape at `sample_qubits` and scales to the full register:
+    every gate / term factor is one pass over 2^n amplitudes, so time scales with 2^n (memory-bound; stated in the
+    `sample` string).  Returns evals/s of the full workload on this host."""
+    from oracle import oracle as O
+    from oracle import oracle_c as OC
+    from qibochem_b200.ansatz._fermion import excitation_generator
+    from qibochem_b200.ansatz.utils import generate_excitations
+    from qibochem_b200.pauli import masks_to_string
+
+    n_full, ns = wl_full["n"], min(sample_qubits, wl_full["n"])
+    nelec_s = max(2, round(wl_full["nelec"] * ns / n_full))
+    nelec_s -= nelec_s % 2
+    # sample rotations: the first double excitations of the (ns, nelec_s) UCCSD order, as reference gate programs
+    excs = generate_excitations(2, range(nelec_s), range(nelec_s, ns))
+    state = np.zeros(1 << ns, dtype=np.complex128)
+    state[0] = 1.0
+    OC.run_gates(state, ns, O.hf_gates(ns, nelec_s))  # also warms the OpenMP pool
+    t_rot, n_rot, n_gates = 0.0, 0, 0
+    for exc in excs:
+        gates = O.ucc_gates(exc, 0.05)
+        t0 = time.perf_counter()
+        OC.run_gates(state, ns, gates)
+        t_rot += time.perf_counter() - t0
+        n_rot += 8
+        n_gates += len(gates)
+        if t_rot > budget_s / 2:
+            break
+    # sample terms: molecular-structured strings on ns qubits, qibo-style (copy + one pass per factor + dot)
+    from qibochem_b200 import synthetic
+    from qibochem_b200.pauli import reverse_bits
+
+    hx, hz, hc, _ = synthetic.molecular_like_hamiltonian(ns, min(wl_full["hx"].size, 2000))
+    pick = np.random.default_rng(0).choice(hx.size, size=min(hx.size, 400), replace=False)
+    tmp = np.empty_like(state)
+    t_term, n_term = 0.0, 0
+    for k in pick:
+        xq, zq = reverse_bits(int(hx[k]), ns), reverse_bits(int(hz[k]), ns)
+        factors = [(int(op[1:]), op[0]) for op in masks_to_string(xq, zq).split()]
+        t0 = time.perf_counter()
+        OC.expectation_terms(state, ns, [(float(hc[k]), factors)], tmp)
+        t_term += time.perf_counter() - t0
+        n_term += 1
+        if t_term > budget_s / 2:
+            break
+    # average factor count differs between n: scale per-term cost by (weight+2) passes (copy, factors, dot)
+    scale = float(2 ** (n_full - ns))
+    # reference gates per rotation grow with n (longer CNOT ladders): use the exact gate census of the full stream
+    full_gates_per_rot = reference_gates_per_rotation(wl_full)
+    t_gate = t_rot / max(n_gates, 1)
+    w_sample = np.mean([bin(int(hx[k]) | int(hz[k])).count("1") + 2 for k in pick[:n_term]])
+    w_full = float(np.mean([bin(int(a) | int(b)).count("1") + 2 for a, b in zip(wl_full["hx"][::97], wl_full["hz"][::97])]))
+    t_eval = scale * (t_gate * full_gates_per_rot * wl_full["rx"].size + (t_term / max(n_term, 1)) * (w_full / w_sample) * wl_full["hx"].size)
+    return {
+        "value": 1.0 / t_eval,
+        "unit": "evals/s",
+        "cores": OC.num_threads(),
+        "kind": "port",
+        "sample": (
+            f"C/OpenMP port of the reference algorithm (in-place gate passes of _expi_pauli programs + qibo-style "
+            f"per-term expectation) timed at {ns} qubits: {n_gates} gate passes ({n_rot} rotations) in {t_rot:.2f}s, "
+            f"{n_term} terms in {t_term:.2f}s; scaled x2^{n_full - ns} (every pass is memory-bound, linear in 2^n), to "
+            f"{full_gates_per_rot:.1f} gates/rotation x {wl_full['rx'].size} rotations and {wl_full['hx'].size} terms of mean "
+            f"{w_full:.1f} passes"
+        ),
+        "seconds_per_eval_extrapolated": t_eval,
+    }
+
+
+def reference_gates_per_rotation(wl: dict) -> float:
+    """Gate count of the reference's `_expi_pauli` program per string (2(nX+2nY) + 2(w-1) + 1, _ansatz.py:73-91)."""
+    tot = 0
+    for x, z in zip(wl["rx"].tolist(), wl["rz"].tolist()):
+        nx, ny, w = bin(x & ~z).count("1"), bin(x & z).count("1"), bin(x | z).count("1")
+        tot += 2 * (nx + 2 * ny) + 2 * (w - 1) + 1
+    return tot / max(1, wl["rx"].size)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def run_reference(args, n, nelec):
+    """--impl reference: the reference's own CPU algorithm on the host cores (oracle port; qibo is not installable)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = workload(n, nelec, args.rotations, args.terms)
+    vals, last = [], None
+    for _ in range(args.warmup):
+        cpu_reference_sample(wl, min(args.cpu_sample_qubits, 22), budget_s=2.0)
+    for _ in range(args.steps):
+        last = cpu_reference_sample(wl, args.cpu_sample_qubits, budget_s=12.0)
+        vals.append(last["value"])
+    v = float(np.mean(vals)) * float(2 ** (n - 30))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "evals/s (30-qubit equivalent)", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / (v / 2 ** (n - 30)), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64 (complex128)", "data": "synthetic",
+        "config": config_dict(wl, args),
+        "cpu_baseline": {**{k: last[k] for k in ("unit", "cores", "kind", "sample")}, "value": v},
+        "e2e": {"value": v, "unit": "evals/s (30-qubit equivalent)", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }  # fmt: skip
+    print(json.dumps(line))
+
+
+def config_dict(wl, args):
+    return {
+        "workload": f"synthetic {wl['n']}-qubit UCCSD-like energy: HF({wl['nelec']}e) + {wl['rx'].size} Pauli rotations "
+        f"({wl['rx'].size // 8} JW doubles, reference order) + {wl['hx'].size + 1}-term molecular-structured Hamiltonian "
+        f"({wl['n_xmasks']} x-masks), complex128",
+        "qubits": wl["n"], "rotations": int(wl["rx"].size), "terms": int(wl["hx"].size + 1), "x_masks": wl["n_xmasks"],
+        "l2": "state (>= 17 GB per GPU) exceeds the 126 MB L2; no flush needed between steps",
+        "sharding": "index bits" if args.gpus > 1 else "none",
+    }  # fmt: skip
+
+
+def main():
+    args = parse_args()
+    n = args.qubits if args.qubits is not None else DEFAULT_QUBITS.get(args.gpus, 30)
+    nelec = args.electrons if args.electrons is not None else {30: 14}.get(n, 2 * ((n * 14 // 30) // 2))
+    if args.impl == "reference":
+        run_reference(args, n, nelec)
+        return
+    if args.gpus > 1:
+        from bench_sharded import main_sharded
+
+        main_sharded(args, n, nelec)
+        return
+
+    import torch
+
+    from qibochem_b200.engine import DeviceState
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the B200 path has no CPU fallback")
+    torch.cuda.set_device(0)
+    wl = workload(n, nelec, args.rotations, args.terms)
+    stream = torch.cuda.Stream()
+    st = DeviceState(n, device=0, stream=stream.cuda_stream)
+
+    def step():
+        st.set_basis_state(wl["hf"])
+        st.apply_pauli_rotations(wl["rx"], wl["rz"], wl["ra"])
+        return wl["const"] + st.expectation(wl["hx"], wl["hz"], wl["hc"])
+
+    energies = [step() for _ in range(args.warmup)]
+    # ---- timed region: K steps, device time from CUDA events on the launching stream
+    st.profile_reset()
+    st.profile_enable(True)
+    clocks = ClockSampler(0)
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        energies.append(step())
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    clock_info = clocks.stop()
+    dev_ms = ev0.elapsed_time(ev1)
+    prof = st.profile()
+    st.profile_enable(False)
+    passes, sweeps = st.last_passes, st.last_sweeps
+    ms_per_step = dev_ms / args.steps
+    value = 1e3 / ms_per_step
+
+    # ---- e2e: the same step through the public Python API (Circuit / SymbolicHamiltonian objects, host arrays in)
+    e2e = measure_e2e(wl, args, st)
+
+    # ---- roofline of the dominant kernel (by device time inside the timed region)
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else None
+    peak = peaks["hbm_gbs"] if peaks else 6650.0
+    dom = max((k for k in prof if prof[k]["launches"]), key=lambda k: prof[k]["ms"])
+    d = prof[dom]
+    achieved = d["bytes"] / 1e9 / (d["ms"] / 1e3) if d["ms"] else 0.0
+    roofline = {
+        "kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "peak_source": "MEASURED_PEAKS.json hbm_gbs (copy, read+write)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
+        "traffic": None,
+        "launches": d["launches"], "avg_launch_ms": d["ms"] / max(d["launches"], 1),
+        "algorithmic_bytes_per_launch": d["bytes"] / max(d["launches"], 1),
+        "share_of_step": d["ms"] / dev_ms,
+        "by_kernel": {k: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps,
+                          "algorithmic_GBps": (v["bytes"] / 1e9 / (v["ms"] / 1e3)) if v["ms"] else None}
+                      for k, v in prof.items() if v["launches"]},
+    }  # fmt: skip
+    launches = int(sum(v["launches"] for v in prof.values()))
+
+    cpu = None if args.no_cpu_baseline else cpu_reference_sample(wl, args.cpu_sample_qubits)
+    line = {
+        "metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64 (complex128)", "data": "synthetic", "config": config_dict(wl, args),
+        "energy": energies[-1], "energy_spread": float(np.ptp(energies)),
+        "passes_per_step": {"k1_rotation_passes": passes, "k2_xmask_sweeps": sweeps},
+        "wall_ms_per_step": 1e3 * wall / args.steps,
+        "clocks": clock_info, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+    }  # fmt: skip
+    print(json.dumps(line))
+
+
+def measure_e2e(wl, args, st):
+    """Energy through the public API: a `Circuit` of PauliRotation gates + `SymbolicHamiltonian.expectation`; every step
+    receives a fresh host parameter vector (`set_parameters`), ships the program to the device and reads the energy
+    back."""
+    from qibochem_b200 import Circuit, SymbolicHamiltonian, gates
+    from qibochem_b200.pauli import masks_to_string, reverse_bits
+    from qibochem_b200.runtime import get_runtime
+
+    n = wl["n"]
+    rt = get_runtime()
+    rt._states[n] = st  # share the already allocated state with the public API's runtime
+    circuit = Circuit(n)
+    circuit.add(gates.X(q) for q in range(wl["nelec"]))
+    for x, z, a in zip(wl["rx"].tolist(), wl["rz"].tolist(), wl["ra"].tolist()):
+        circuit.add(gates.PauliRotation(masks_to_string(reverse_bits(x, n), reverse_bits(z, n)), a))
+    ham = SymbolicHamiltonian.from_index_masks(n, wl["hx"], wl["hz"], wl["hc"], constant=wl["const"])
+    rng = np.random.default_rng(0)
+    params = [wl["ra"] * (1.0 + 1e-3 * rng.normal()) for _ in range(args.steps + 1)]
+    circuit.set_parameters(params[0])
+    ham.expectation(circuit)  # warm-up (compiles the program)
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        circuit.set_parameters(params[k + 1])
+        ham.expectation(circuit)
+    dt = (time.perf_counter() - t0) / args.steps
+    rt._states.pop(n, None)
+    h2d = int(wl["rx"].size * 24 + wl["hx"].size * 24)
+    return {"value": 1.0 / dt, "unit": "evals/s", "ms_per_step": 1e3 * dt, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 16,
+            "api": "Circuit.set_parameters(host array) + SymbolicHamiltonian.expectation(circuit) -> float"}  # fmt: skip
+
+
+if __name__ == "__main__":
+    main()

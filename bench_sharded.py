@@ -1,0 +1,102 @@
+"""bench.py's N > 1 arm: one rank per GPU (torchrun), state sharded on the top log2(N) index bits."""
+
+from __future__ import annotations
+
+import json
+import os
+import time
+
+import numpy as np
+
+
+def main_sharded(args, n: int, nelec: int) -> None:
+    import torch
+    import torch.distributed as dist
+
+    from bench import METRIC, ClockSampler, config_dict, workload
+    from qibochem_b200.engine import DeviceState
+    from qibochem_b200.sharded import IpcExchanger, ShardedState
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    local_rank = int(os.environ.get("LOCAL_RANK", str(rank)))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29511")
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{local_rank}"))
+    g = world.bit_length() - 1
+    wl = workload(n, nelec, args.rotations, args.terms)
+    stream = torch.cuda.Stream()
+    local = DeviceState(n - g, device=local_rank, stream=stream.cuda_stream)
+    ex = IpcExchanger(local, rank, world, local_rank)
+    st = ShardedState(n, rank, world, local, ex, min_swap_pos=8)
+
+    def step():
+        st.set_basis_state(wl["hf"])
+        st.apply_pauli_rotations(wl["rx"], wl["rz"], wl["ra"])
+        return wl["const"] + st.expectation(wl["hx"], wl["hz"], wl["hc"])
+
+    energies = [step() for _ in range(args.warmup)]
+    local.profile_reset()
+    local.profile_enable(True)
+    ex.swap_seconds, ex.swap_bytes = 0.0, 0
+    swaps0 = st.n_swaps
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+    ex.barrier()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        energies.append(step())
+    ev1.record(stream)
+    ex.barrier()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    dev_ms = ev0.elapsed_time(ev1)
+    t = torch.tensor([dev_ms, 1e3 * wall], dtype=torch.float64, device=f"cuda:{local_rank}")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, wall_ms = float(t[0]), float(t[1])
+    prof = local.profile()
+    local.profile_enable(False)
+    clock_info = clocks.stop() if clocks else None
+    swaps = st.n_swaps - swaps0
+
+    if rank == 0:
+        scale = float(2 ** (n - 30))
+        ms_per_step = dev_ms / args.steps
+        peaks_path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "MEASURED_PEAKS.json")
+        peaks = json.load(open(peaks_path)) if os.path.exists(peaks_path) else None
+        peak = peaks["hbm_gbs"] if peaks else 6650.0
+        dom = max((k for k in prof if prof[k]["launches"]), key=lambda k: prof[k]["ms"])
+        d = prof[dom]
+        achieved = d["bytes"] / 1e9 / (d["ms"] / 1e3) if d["ms"] else 0.0
+        nvlink = (ex.swap_bytes / 1e9 / ex.swap_seconds) if ex.swap_seconds else None
+        line = {
+            "metric": METRIC, "value": scale * 1e3 / ms_per_step, "unit": "evals/s (30-qubit equivalent: x 2^(n-30))",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 (complex128)",
+            "data": "synthetic", "config": config_dict(wl, args),
+            "raw_evals_per_sec": 1e3 / ms_per_step, "energy": energies[-1], "energy_spread": float(np.ptp(energies)),
+            "clocks": clock_info,
+            "e2e": {"value": scale * 1e3 * args.steps / wall_ms, "unit": "evals/s (30-qubit equivalent)",
+                    "h2d_bytes_per_step": int(wl["rx"].size * 24 + wl["hx"].size * 24) * world, "d2h_bytes_per_step": 8 * world,
+                    "api": "ShardedState.apply_pauli_rotations / expectation with host arrays, host wall clock, max over ranks"},
+            "gpu_launches": int(sum(v["launches"] for v in prof.values())) * world,
+            "roofline": {
+                "kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "scope": "rank 0, per GPU", "traffic": None, "launches": d["launches"],
+                "avg_launch_ms": d["ms"] / max(d["launches"], 1), "share_of_step": d["ms"] / dev_ms,
+                "by_kernel": {k: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps,
+                                  "algorithmic_GBps": (v["bytes"] / 1e9 / (v["ms"] / 1e3)) if v["ms"] else None}
+                              for k, v in prof.items() if v["launches"]},
+            },
+            "exchange": {"global_bit_swaps_per_step": swaps / args.steps, "bytes_out_per_gpu_per_swap": local.dim * 8,
+                         "nvlink_GBps_per_direction_incl_barriers": nvlink, "nvlink_peak_GBps": 770.0},
+            "cpu_baseline": None,
+        }  # fmt: skip
+        print(json.dumps(line))
+    ex.close()
+    dist.destroy_process_group()

@@ -91,6 +91,14 @@ int qc_parity_sums(qc_state* h, const uint64_t* samples, const int64_t* counts, 
 int qc_frequencies(qc_state* h, const uint64_t* samples, size_t n, int on_device, uint64_t keep_mask,
                    uint64_t* keys_out, int64_t* counts_out, size_t cap, size_t* n_unique_out);
 
+/* ---- live profiler / launch counter (bench.py: roofline of the dominant kernel, gpu_launches) ----------------- */
+/* Kernel classes: 0 K0 init, 1 K1 rotation pass, 2 K2 expectation sweeps, 3 reductions, 4 K5 sampling, 5 K3 shot
+ * statistics, 6 K4 exchange.  Launch counts and algorithmic bytes are always accumulated; when enabled, every
+ * launch is additionally bracketed by CUDA events on the handle's stream and its device time accumulated. */
+int qc_profile_enable(qc_state* h, int enabled);
+int qc_profile_reset(qc_state* h);
+int qc_profile_get(qc_state* h, int kernel_class, double* ms_total, uint64_t* launches, double* algorithmic_bytes);
+
 /* ---- host <-> device copies of amplitudes (tests, checkpoints; n <= ~30) ----------------------------------- */
 /* interleaved (re, im) doubles */
 int qc_copy_state_to_host(qc_state* h, double* out, uint64_t offset, uint64_t count);

@@ -40,6 +40,25 @@ struct Arena {
     void release();
 };
 
+// Kernel classes for the launch counter / live profiler (qc_profile_*)
+enum KernelClass { kK0Init = 0, kK1Rotation = 1, kK2Expectation = 2, kReduce = 3, kK5Sampling = 4, kK3Shots = 5, kK4Exchange = 6, kNumClasses = 7 };
+
+struct Profiler {
+    bool enabled = false;
+    struct Rec {
+        int cls;
+        cudaEvent_t a, b;
+    };
+    std::vector<Rec> pending;
+    std::vector<cudaEvent_t> pool;
+    double ms[kNumClasses] = {0};
+    double bytes[kNumClasses] = {0};       // algorithmic bytes, counted always
+    uint64_t launches[kNumClasses] = {0};  // counted always
+    cudaEvent_t get_event();
+    void collect();  // caller has synchronised the stream
+    void release();
+};
+
 constexpr int kThreads = 256;       // threads per CTA for the sweep kernels
 constexpr int kCtasPerSm = 8;       // 8 x 256 = 2048 resident threads per SM
 
@@ -60,6 +79,7 @@ struct qc_state {
     size_t out_cap = 0;
     double* h_out = nullptr;       // pinned mirror of d_out
     double2* scratch_psi = nullptr;  // scratch copy of the shard (sampling), allocated lazily
+    qc::Profiler prof;
     int ensure_partials(size_t doubles);
     int ensure_out(size_t doubles);
 };
@@ -108,6 +128,27 @@ __device__ __forceinline__ double block_sum(double v) {
     }
     return t;
 }
+
+// RAII bracket around one kernel launch: counts it and, when profiling is on, times it with CUDA events recorded
+// on the handle's stream.
+struct LaunchScope {
+    qc_state* h;
+    int cls;
+    cudaEvent_t stop = nullptr;
+    LaunchScope(qc_state* h_, int cls_, double algorithmic_bytes) : h(h_), cls(cls_) {
+        h->prof.launches[cls] += 1;
+        h->prof.bytes[cls] += algorithmic_bytes;
+        if (h->prof.enabled) {
+            cudaEvent_t a = h->prof.get_event();
+            stop = h->prof.get_event();
+            cudaEventRecord(a, h->stream);
+            h->prof.pending.push_back({cls, a, stop});
+        }
+    }
+    ~LaunchScope() {
+        if (stop) cudaEventRecord(stop, h->stream);
+    }
+};
 
 // out[g] = sum_b partials[g*stride + b] (one CTA per g, fixed order); defined in state.cu
 int fold_partials(qc_state* h, const double* partials, int ngroups, int nb, int stride, double* out);

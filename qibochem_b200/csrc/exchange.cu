@@ -11,6 +11,8 @@
 // one rank (rank side s handles the pairs p with p's top bit == s... see `part`), reading one local and one remote
 // amplitude and writing both, so the exchange needs no staging buffer and each NVLink direction carries the
 // minimum of B_local/2 bytes per rank (half as read responses, half as writes).
+#include <string.h>
+
 #include "common.cuh"
 
 namespace qc {
@@ -88,6 +90,7 @@ int qc_swap_with_peer(qc_state* h, void* peer_ptr, int local_bit, int my_side, i
     double2* a = my_side == 0 ? h->psi : (double2*)peer_ptr;
     double2* b = my_side == 0 ? (double2*)peer_ptr : h->psi;
     const int nb = grid_for(p_end - p_begin, 4, h->sm_count);
+    LaunchScope ls(h, kK4Exchange, 32.0 * (double)(p_end - p_begin));
     swap_bit_kernel<4><<<nb, kThreads, 0, h->stream>>>(a, b, p_begin, p_end, local_bit);
     QC_CHECK(cudaGetLastError());
     return 0;
@@ -102,6 +105,7 @@ int qc_swap_local_pair(qc_state* lo, qc_state* hi, int local_bit) {
     QC_CHECK(cudaStreamSynchronize(hi->stream));
     const uint64_t npairs = lo->dim >> 1;
     const int nb = grid_for(npairs, 4, lo->sm_count);
+    LaunchScope ls(lo, kK4Exchange, 32.0 * (double)npairs);
     swap_bit_kernel<4><<<nb, kThreads, 0, lo->stream>>>(lo->psi, hi->psi, 0, npairs, local_bit);
     QC_CHECK(cudaGetLastError());
     QC_CHECK(cudaStreamSynchronize(lo->stream));

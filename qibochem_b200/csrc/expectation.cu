@@ -10,6 +10,8 @@
 //   nY even:  pair contribution = 2 (-1)^{nY/2}      s(i) Re q_i
 //   nY odd :  pair contribution = 2 (-1)^{(nY-1)/2}  s(i) Im q_i
 // so each term is a real weight d_k = c_k (-1)^{floor(nY/2)} applied to Re q or Im q.
+#include <string.h>
+
 #include <algorithm>
 #include <numeric>
 
@@ -202,7 +204,10 @@ extern "C" int qc_expectation(qc_state* h, size_t T, const uint64_t* xmask, cons
     for (size_t g0 = 0; g0 < ng; g0 += chunk) {
         const size_t gn = std::min(chunk, ng - g0);
         dim3 grid(nbx, (unsigned)gn);
-        expectation_kernel<4><<<grid, kThreads, 0, h->stream>>>(h->psi, h->dim, dgroups + g0, dterms, h->d_partials);
+        {
+            LaunchScope ls(h, kK2Expectation, 16.0 * (double)h->dim * (double)gn);  // one read sweep per x-group
+            expectation_kernel<4><<<grid, kThreads, 0, h->stream>>>(h->psi, h->dim, dgroups + g0, dterms, h->d_partials);
+        }
         QC_CHECK(cudaGetLastError());
         if (fold_partials(h, h->d_partials, (int)gn, nbx, nbx, h->d_out + 1 + g0)) return 1;
     }

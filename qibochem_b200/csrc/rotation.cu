@@ -229,6 +229,7 @@ extern "C" int qc_apply_pauli_rotations(qc_state* h, size_t R, const uint64_t* x
     const double2* dtab = (const double2*)h->arena.dev;
 
     for (const RotDesc& d : descs) {
+        LaunchScope ls(h, kK1Rotation, 32.0 * (double)h->dim);  // every amplitude read + written once per pass
         if (d.x == 0) {
             const int nb = grid_for(h->dim, 4, h->sm_count);
             rot_diag_kernel<4><<<nb, kThreads, 0, h->stream>>>(h->psi, h->dim, d, dtab);

@@ -73,6 +73,7 @@ __global__ void __launch_bounds__(kThreads) gate1q_low_kernel(double2* __restric
 }
 
 static int apply_gate1q(qc_state* h, double2* psi, int bit, const Mat2& m) {
+    LaunchScope ls(h, kK5Sampling, 32.0 * (double)h->dim);
     if (bit < 5) {
         const int nb = grid_for(h->dim, 4, h->sm_count);
         gate1q_low_kernel<<<nb, kThreads, 0, h->stream>>>(psi, h->dim, bit, m);
@@ -325,9 +326,15 @@ int qc_sample(qc_state* h, uint64_t x_basis_mask, uint64_t y_basis_mask, size_t 
     const uint64_t nchunks = h->dim >> chunk_log2;
     if (h->ensure_partials(nchunks)) return 1;
     const int nb = (int)std::min<uint64_t>(nchunks, (uint64_t)h->sm_count * kCtasPerSm);
-    chunk_prob_kernel<<<nb, kThreads, 0, h->stream>>>(src, h->dim, chunk_log2, h->d_partials);
+    {
+        LaunchScope ls(h, kK5Sampling, 16.0 * (double)h->dim);
+        chunk_prob_kernel<<<nb, kThreads, 0, h->stream>>>(src, h->dim, chunk_log2, h->d_partials);
+    }
     QC_CHECK(cudaGetLastError());
-    inclusive_scan_kernel<<<1, 1024, 0, h->stream>>>(h->d_partials, nchunks);
+    {
+        LaunchScope ls(h, kK5Sampling, 0.0);
+        inclusive_scan_kernel<<<1, 1024, 0, h->stream>>>(h->d_partials, nchunks);
+    }
     QC_CHECK(cudaGetLastError());
     if (total_prob_out) {
         if (h->ensure_out(1)) return 1;
@@ -338,8 +345,10 @@ int qc_sample(qc_state* h, uint64_t x_basis_mask, uint64_t y_basis_mask, size_t 
         if (!samples_on_device) QC_CHECK(cudaMalloc(&dsamples, n_shots * sizeof(uint64_t)));
         const uint64_t warps_needed = n_shots;
         const uint64_t ctas = std::min<uint64_t>((warps_needed * 32 + kThreads - 1) / kThreads, (uint64_t)h->sm_count * kCtasPerSm);
+        LaunchScope* ls = new LaunchScope(h, kK5Sampling, 0.0);
         sample_kernel<<<(int)ctas, kThreads, 0, h->stream>>>(src, chunk_log2, h->d_partials, nchunks, n_shots, seed,
                                                              shot_offset, dsamples);
+        delete ls;
         cudaError_t e = cudaGetLastError();
         if (e == cudaSuccess && !samples_on_device)
             e = cudaMemcpyAsync(samples_out, dsamples, n_shots * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream);
@@ -387,6 +396,7 @@ int qc_parity_sums(qc_state* h, const uint64_t* samples, const int64_t* counts, 
     }
     if (e == cudaSuccess) {
         const int nb = grid_for(n, 8, h->sm_count);
+        LaunchScope ls(h, kK3Shots, 8.0 * (double)n);
         parity_sums_kernel<<<nb, kThreads, 0, h->stream>>>(dsamples, dcounts, n, dmasks, (uint32_t)J, dS);
         e = cudaGetLastError();
     }
@@ -423,6 +433,7 @@ int qc_frequencies(qc_state* h, const uint64_t* samples, size_t n, int on_device
         e = cudaMalloc(&dbins, nbins * sizeof(unsigned long long));
         if (e == cudaSuccess) e = cudaMemsetAsync(dbins, 0, nbins * sizeof(unsigned long long), h->stream);
         if (e == cudaSuccess) {
+            LaunchScope ls(h, kK3Shots, 8.0 * (double)n);
             histogram_direct_kernel<<<nb, kThreads, 0, h->stream>>>(dsamples, n, keep_mask, dbins);
             e = cudaGetLastError();
         }
@@ -442,6 +453,7 @@ int qc_frequencies(qc_state* h, const uint64_t* samples, size_t n, int on_device
         if (e == cudaSuccess) e = cudaMemsetAsync(dk, 0xff, capacity * sizeof(unsigned long long), h->stream);
         if (e == cudaSuccess) e = cudaMemsetAsync(dc, 0, capacity * sizeof(unsigned long long), h->stream);
         if (e == cudaSuccess) {
+            LaunchScope ls(h, kK3Shots, 8.0 * (double)n);
             histogram_hash_kernel<<<nb, kThreads, 0, h->stream>>>(dsamples, n, keep_mask, dk, dc, capacity - 1);
             e = cudaGetLastError();
         }

@@ -23,6 +23,35 @@ void Arena::release() {
     cap = 0;
 }
 
+cudaEvent_t Profiler::get_event() {
+    if (!pool.empty()) {
+        cudaEvent_t e = pool.back();
+        pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+void Profiler::collect() {
+    for (const Rec& r : pending) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) ms[r.cls] += t;
+        pool.push_back(r.a);
+        pool.push_back(r.b);
+    }
+    pending.clear();
+}
+void Profiler::release() {
+    for (const Rec& r : pending) {
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    for (cudaEvent_t e : pool) cudaEventDestroy(e);
+    pending.clear();
+    pool.clear();
+}
+
 __global__ void set_one_kernel(double2* psi, uint64_t index) { psi[index] = make_double2(1.0, 0.0); }
 
 __global__ void __launch_bounds__(kThreads) norm2_kernel(const double2* __restrict__ psi, uint64_t dim,
@@ -47,6 +76,7 @@ __global__ void __launch_bounds__(kThreads) fold_partials_kernel(const double* _
 }
 
 int fold_partials(qc_state* h, const double* partials, int ngroups, int nb, int stride, double* out) {
+    LaunchScope ls(h, kReduce, 0.0);
     fold_partials_kernel<<<ngroups, kThreads, 0, h->stream>>>(partials, nb, stride, out);
     QC_CHECK(cudaGetLastError());
     return 0;
@@ -137,6 +167,7 @@ int qc_destroy(qc_state* h) {
     if (h->d_out) cudaFree(h->d_out);
     if (h->h_out) cudaFreeHost(h->h_out);
     h->arena.release();
+    h->prof.release();
     if (h->owns_stream) cudaStreamDestroy(h->stream);
     delete h;
     return 0;
@@ -161,7 +192,9 @@ int qc_set_basis_state(qc_state* h, uint64_t index, int has_one) {
     QC_REQUIRE(!has_one || index < h->dim, "qc_set_basis_state: index out of range");
     QC_CHECK(cudaSetDevice(h->device));
     QC_CHECK(cudaMemsetAsync(h->psi, 0, h->dim * sizeof(double2), h->stream));
+    h->prof.bytes[qc::kK0Init] += 16.0 * (double)h->dim;  // the memset writes the shard once
     if (has_one) {
+        qc::LaunchScope ls(h, qc::kK0Init, 0.0);
         qc::set_one_kernel<<<1, 1, 0, h->stream>>>(h->psi, index);
         QC_CHECK(cudaGetLastError());
     }
@@ -173,12 +206,46 @@ int qc_norm2(qc_state* h, double* out) {
     QC_CHECK(cudaSetDevice(h->device));
     const int nb = qc::grid_for(h->dim, 4, h->sm_count);
     if (h->ensure_partials(nb) || h->ensure_out(1)) return 1;
-    qc::norm2_kernel<<<nb, qc::kThreads, 0, h->stream>>>(h->psi, h->dim, h->d_partials);
+    {
+        qc::LaunchScope ls(h, qc::kReduce, 16.0 * (double)h->dim);
+        qc::norm2_kernel<<<nb, qc::kThreads, 0, h->stream>>>(h->psi, h->dim, h->d_partials);
+    }
     QC_CHECK(cudaGetLastError());
     if (qc::fold_partials(h, h->d_partials, 1, nb, nb, h->d_out)) return 1;
     QC_CHECK(cudaMemcpyAsync(h->h_out, h->d_out, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     QC_CHECK(cudaStreamSynchronize(h->stream));
     *out = h->h_out[0];
+    return 0;
+}
+
+int qc_profile_enable(qc_state* h, int enabled) {
+    QC_REQUIRE(h, "qc_profile_enable: null handle");
+    h->prof.enabled = enabled != 0;
+    return 0;
+}
+
+int qc_profile_reset(qc_state* h) {
+    QC_REQUIRE(h, "qc_profile_reset: null handle");
+    QC_CHECK(cudaSetDevice(h->device));
+    QC_CHECK(cudaStreamSynchronize(h->stream));
+    h->prof.collect();
+    for (int c = 0; c < qc::kNumClasses; ++c) {
+        h->prof.ms[c] = 0.0;
+        h->prof.bytes[c] = 0.0;
+        h->prof.launches[c] = 0;
+    }
+    return 0;
+}
+
+int qc_profile_get(qc_state* h, int kernel_class, double* ms_total, uint64_t* launches, double* algorithmic_bytes) {
+    QC_REQUIRE(h, "qc_profile_get: null handle");
+    QC_REQUIRE(kernel_class >= 0 && kernel_class < qc::kNumClasses, "qc_profile_get: bad kernel class");
+    QC_CHECK(cudaSetDevice(h->device));
+    QC_CHECK(cudaStreamSynchronize(h->stream));
+    h->prof.collect();
+    if (ms_total) *ms_total = h->prof.ms[kernel_class];
+    if (launches) *launches = h->prof.launches[kernel_class];
+    if (algorithmic_bytes) *algorithmic_bytes = h->prof.bytes[kernel_class];
     return 0;
 }
 

@@ -210,6 +210,24 @@ class DeviceState:
             "qc_copy_state_from_host",
         )  # fmt: skip
 
+    # -- profiler ----------------------------------------------------------------------------------------------
+    KERNEL_CLASSES = ("k0_init", "k1_rotation", "k2_expectation", "reduce", "k5_sampling", "k3_shots", "k4_exchange")
+
+    def profile_enable(self, enabled: bool = True) -> None:
+        _native.check(self._lib.qc_profile_enable(self._h, int(enabled)), "qc_profile_enable")
+
+    def profile_reset(self) -> None:
+        _native.check(self._lib.qc_profile_reset(self._h), "qc_profile_reset")
+
+    def profile(self) -> dict:
+        """{class: {"ms": device time (0 unless enabled), "launches": n, "bytes": algorithmic bytes}}"""
+        out = {}
+        for k, name in enumerate(self.KERNEL_CLASSES):
+            ms, n, b = C.c_double(0.0), C.c_uint64(0), C.c_double(0.0)
+            _native.check(self._lib.qc_profile_get(self._h, k, C.byref(ms), C.byref(n), C.byref(b)), "qc_profile_get")
+            out[name] = {"ms": ms.value, "launches": n.value, "bytes": b.value}
+        return out
+
     # -- K4 ---------------------------------------------------------------------------------------------------
     def ipc_export(self) -> bytes:
         buf = C.create_string_buffer(64)

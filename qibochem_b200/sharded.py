@@ -1,0 +1,262 @@
+"""
+State sharding over G = 2^g GPUs, one process per GPU (the reference is single-process and has no
+counterpart).
+
+The amplitude index is split into ``n - g`` LOCAL bits (inside a shard) and ``g`` GLOBAL bits (the rank).  Which
+*logical* index bit (logical bit b <-> qubit n-1-b) sits at which *physical* position is a permutation owned by the
+host; masks are translated per call.  Consequences for a Pauli string (x, z):
+
+* z on a global bit  -> a per-rank constant sign, folded into the rotation angle / term coefficient (no traffic);
+* x on a global bit  -> the partner shard's amplitudes are needed: the global bit is first exchanged with a local
+  bit that the upcoming strings do not pair on (``qc_swap_with_peer``: in-place peer-memory swap of half a shard
+  over NVLink), after which every local kernel runs unchanged.  Evictions follow Belady's rule (farthest next use).
+
+The exact energy finishes with one scalar all-reduce.  ``ShardedState`` only needs a *local shard* (``DeviceState``
+API) and an *exchanger* (swap + all-reduce + barrier), so the host logic is testable on CPU with gloo.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+
+def _bits(mask: int):
+    b = 0
+    while mask >> b:
+        if (mask >> b) & 1:
+            yield b
+        b += 1
+
+
+class ShardedState:
+    """n-qubit state over ``world`` = 2^g ranks.
+
+    Args:
+        n_qubits: total qubits
+        rank, world: this process' rank and the (power of two) number of ranks
+        local: object with the ``DeviceState`` API holding 2^(n-g) amplitudes
+        exchanger: object with ``swap(global_k, local_pos)``, ``allreduce_sum(float) -> float``, ``barrier()``
+        min_swap_pos: lowest local physical position eligible for an exchange (keeps peer accesses in long runs)
+    """
+
+    def __init__(self, n_qubits: int, rank: int, world: int, local, exchanger, min_swap_pos: int = 0):
+        g = world.bit_length() - 1
+        if 1 << g != world:
+            raise ValueError("the number of ranks must be a power of two")
+        if n_qubits - g < 1:
+            raise ValueError("too many ranks for this register")
+        self.n, self.g, self.nl = n_qubits, g, n_qubits - g
+        self.rank, self.world = rank, world
+        self.local, self.ex = local, exchanger
+        self.min_swap_pos = min(min_swap_pos, self.nl - 1)
+        self.pos = list(range(n_qubits))  # pos[logical bit] = physical position (>= nl: global bit pos-nl of the rank)
+        self.n_swaps = 0
+        self.last_passes = 0
+        self.last_sweeps = 0
+
+    # ---- layout ---------------------------------------------------------------------------------------------
+    def _is_global(self, logical_bit: int) -> bool:
+        return self.pos[logical_bit] >= self.nl
+
+    def _global_mask(self) -> int:
+        return sum(1 << b for b in range(self.n) if self._is_global(b))
+
+    def _to_physical(self, mask: int) -> tuple[int, int]:
+        """logical mask -> (local physical mask, global part as a mask over rank bits)"""
+        loc = glob = 0
+        for b in _bits(mask):
+            p = self.pos[b]
+            if p < self.nl:
+                loc |= 1 << p
+            else:
+                glob |= 1 << (p - self.nl)
+        return loc, glob
+
+    def _rank_sign(self, global_part: int) -> float:
+        return -1.0 if bin(self.rank & global_part).count("1") & 1 else 1.0
+
+    def _swap(self, global_logical: int, local_logical: int) -> None:
+        """Exchange a global logical bit with a local one (data movement + permutation update)."""
+        pg, pl = self.pos[global_logical], self.pos[local_logical]
+        assert pg >= self.nl > pl
+        self.ex.swap(pg - self.nl, pl)
+        self.pos[global_logical], self.pos[local_logical] = pl, pg
+        self.n_swaps += 1
+
+    def _localise(self, needed_mask: int, future_x: list[int], protect_mask: int = 0) -> None:
+        """Make every logical bit of `needed_mask` local, evicting the local bits whose next pairing use in
+        `future_x` is farthest away (never one of `needed_mask | protect_mask`)."""
+        todo = [b for b in _bits(needed_mask) if self._is_global(b)]
+        if not todo:
+            return
+        banned = needed_mask | protect_mask
+        candidates = [b for b in range(self.n) if not self._is_global(b) and not (banned >> b) & 1 and self.pos[b] >= self.min_swap_pos]
+        if len(candidates) < len(todo):
+            candidates = [b for b in range(self.n) if not self._is_global(b) and not (needed_mask >> b) & 1]
+        if len(candidates) < len(todo):
+            raise ValueError("a single Pauli string pairs on more bits than fit in one shard")
+        next_use = {}
+        for b in candidates:
+            nu = len(future_x)
+            for k, fx in enumerate(future_x):
+                if (fx >> b) & 1:
+                    nu = k
+                    break
+            next_use[b] = nu
+        candidates.sort(key=lambda b: (-next_use[b], -self.pos[b]))
+        for gb, lb in zip(todo, candidates):
+            self._swap(gb, lb)
+
+    # ---- K0 ---------------------------------------------------------------------------------------------------
+    def set_basis_state(self, index: int) -> None:
+        loc, glob = self._to_physical(index)
+        self.local.set_basis_state(loc, has_one=(glob == self.rank))
+
+    # ---- K1 ---------------------------------------------------------------------------------------------------
+    def apply_pauli_rotations(self, xmask, zmask, angle, lookahead: int = 4096) -> int:
+        xs = [int(v) for v in np.asarray(xmask, dtype=np.uint64).tolist()]
+        zs = [int(v) for v in np.asarray(zmask, dtype=np.uint64).tolist()]
+        ang = np.asarray(angle, dtype=np.float64)
+        R = len(xs)
+        passes = 0
+        i = 0
+        while i < R:
+            gm = self._global_mask()
+            if xs[i] & gm:
+                self._localise(xs[i], xs[i + 1 : i + 1 + lookahead])
+                gm = self._global_mask()
+            j = i
+            while j < R and not (xs[j] & gm):
+                j += 1
+            px = np.empty(j - i, dtype=np.uint64)
+            pz = np.empty(j - i, dtype=np.uint64)
+            pa = np.empty(j - i, dtype=np.float64)
+            for k in range(i, j):
+                xl, _ = self._to_physical(xs[k])
+                zl, zg = self._to_physical(zs[k])
+                px[k - i], pz[k - i] = xl, zl
+                pa[k - i] = ang[k] * self._rank_sign(zg)
+            passes += self.local.apply_pauli_rotations(px, pz, pa)
+            i = j
+        self.last_passes = passes
+        return passes
+
+    # ---- K2 ---------------------------------------------------------------------------------------------------
+    def expectation(self, xmask, zmask, coeff) -> float:
+        """sum_k c_k Re<psi|P_k|psi> over the whole register (identical on every rank after the all-reduce)."""
+        xs = np.asarray(xmask, dtype=np.uint64)
+        zs = np.asarray(zmask, dtype=np.uint64)
+        cs = np.asarray(coeff, dtype=np.float64)
+        remaining = np.ones(xs.size, dtype=bool)
+        partial = 0.0
+        sweeps = 0
+        while remaining.any():
+            gm = np.uint64(self._global_mask())
+            ready = remaining & ((xs & gm) == 0)
+            if not ready.any():
+                self._relayout_for_terms(xs[remaining])
+                gm = np.uint64(self._global_mask())
+                ready = remaining & ((xs & gm) == 0)
+                if not ready.any():
+                    raise RuntimeError("could not find a layout that makes any remaining term local")
+            idx = np.nonzero(ready)[0]
+            px, pz, pc = self._translate_terms(xs[idx], zs[idx], cs[idx])
+            partial += self.local.expectation(px, pz, pc)
+            sweeps += self.local.last_sweeps
+            remaining[idx] = False
+        self.last_sweeps = sweeps
+        return self.ex.allreduce_sum(partial)
+
+    def _translate_terms(self, xs, zs, cs):
+        """Vectorised logical -> physical translation of term masks + rank signs."""
+        px = np.zeros(xs.size, dtype=np.uint64)
+        pz = np.zeros(xs.size, dtype=np.uint64)
+        par = np.zeros(xs.size, dtype=np.uint64)
+        one = np.uint64(1)
+        for b in range(self.n):
+            p = self.pos[b]
+            xb = (xs >> np.uint64(b)) & one
+            zb = (zs >> np.uint64(b)) & one
+            if p < self.nl:
+                px |= xb << np.uint64(p)
+                pz |= zb << np.uint64(p)
+            elif (self.rank >> (p - self.nl)) & 1:
+                par ^= zb
+        return px, pz, np.where(par == 1, -cs, cs)
+
+    def _relayout_for_terms(self, xs_remaining: np.ndarray) -> None:
+        """Choose as global the g logical bits on which the fewest remaining terms pair, then swap them out."""
+        usage = [(int(((xs_remaining >> np.uint64(b)) & np.uint64(1)).sum()), b) for b in range(self.n)]
+        usage.sort()
+        want_global = [b for _, b in usage[: self.g]]
+        cur_global = [b for b in range(self.n) if self._is_global(b)]
+        incoming = [b for b in cur_global if b not in want_global]  # become local
+        outgoing = [b for b in want_global if b not in cur_global]  # become global
+        for gb, lb in zip(incoming, outgoing):
+            self._swap(gb, lb)
+
+    def norm2(self) -> float:
+        return self.ex.allreduce_sum(self.local.norm2())
+
+    # ---- tests / small registers ------------------------------------------------------------------------------
+    def gather_logical(self) -> np.ndarray:
+        """Full state in LOGICAL index order on every rank (small n only; used by tests)."""
+        shard = self.local.to_numpy()
+        full_phys = self.ex.allgather_array(shard)  # physical order: rank-major
+        idx = np.arange(1 << self.n, dtype=np.uint64)
+        phys = np.zeros_like(idx)
+        for b in range(self.n):
+            phys |= ((idx >> np.uint64(b)) & np.uint64(1)) << np.uint64(self.pos[b])
+        return full_phys[phys]
+
+
+class IpcExchanger:
+    """Exchanger for one-process-per-GPU runs: torch.distributed (NCCL) for barriers / all-reduce, CUDA IPC peer
+    pointers + the in-place swap kernel for the data movement."""
+
+    def __init__(self, state, rank: int, world: int, device: int):
+        import torch
+        import torch.distributed as dist
+
+        self.torch, self.dist = torch, dist
+        self.state, self.rank, self.world, self.device = state, rank, world, device
+        handles = [None] * world
+        dist.all_gather_object(handles, state.ipc_export())
+        self.peer = {r: state.ipc_open(handles[r]) for r in range(world) if r != rank}
+        self._buf = torch.zeros(1, dtype=torch.float64, device=f"cuda:{device}")
+        self.swap_seconds = 0.0
+        self.swap_bytes = 0
+
+    def barrier(self) -> None:
+        self.state.synchronize()
+        self.dist.all_reduce(self._buf)  # NCCL barrier on torch's stream
+        self.torch.cuda.current_stream().synchronize()
+
+    def swap(self, global_k: int, local_pos: int) -> None:
+        import time
+
+        partner = self.rank ^ (1 << global_k)
+        side = (self.rank >> global_k) & 1
+        self.barrier()  # both shards idle and consistent
+        t0 = time.perf_counter()
+        self.state.swap_with_peer(self.peer[partner], local_pos, side, side)
+        self.barrier()  # both halves of the exchange have landed
+        self.swap_seconds += time.perf_counter() - t0
+        self.swap_bytes += self.state.dim * 16 // 2  # bytes leaving (= entering) this GPU
+
+    def allreduce_sum(self, value: float) -> float:
+        t = self.torch.tensor([value], dtype=self.torch.float64, device=f"cuda:{self.device}")
+        self.dist.all_reduce(t)
+        return float(t.item())
+
+    def allgather_array(self, arr: np.ndarray) -> np.ndarray:
+        t = self.torch.from_numpy(np.ascontiguousarray(arr).view(np.float64)).to(f"cuda:{self.device}")
+        out = [self.torch.empty_like(t) for _ in range(self.world)]
+        self.dist.all_gather(out, t)
+        return np.concatenate([o.cpu().numpy().view(np.complex128) for o in out])
+
+    def close(self) -> None:
+        self.barrier()
+        for p in self.peer.values():
+            self.state.ipc_close(p)
+        self.peer = {}

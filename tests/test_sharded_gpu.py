@@ -1,0 +1,108 @@
+"""Sharded path on the GPU.  (1) Two / four ranks emulated as threads of one process on ONE GPU: every rank owns a
+DeviceState and the real peer-swap kernel runs on the other rank's device pointer.  (2) With >= 2 GPUs: the real
+one-process-per-GPU launch (torchrun, NCCL, CUDA IPC)."""
+
+import os
+import subprocess
+import sys
+import threading
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from tests.test_sharded_cpu import _inputs
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class ThreadExchanger:
+    """All ranks live in one process; collectives are a threading.Barrier plus shared slots."""
+
+    def __init__(self, rank, world, states, barrier, slots):
+        self.rank, self.world, self.states, self.bar, self.slots = rank, world, states, barrier, slots
+
+    def barrier(self):
+        self.states[self.rank].synchronize()
+        self.bar.wait()
+
+    def swap(self, global_k, local_pos):
+        partner = self.rank ^ (1 << global_k)
+        side = (self.rank >> global_k) & 1
+        self.barrier()
+        self.states[self.rank].swap_with_peer(self.states[partner].device_ptr, local_pos, side, side)
+        self.barrier()
+
+    def allreduce_sum(self, value):
+        self.slots[self.rank] = value
+        self.bar.wait()
+        total = sum(self.slots[r] for r in range(self.world))  # fixed order on every rank
+        self.bar.wait()
+        return total
+
+    def allgather_array(self, arr):
+        self.slots[self.rank] = arr
+        self.bar.wait()
+        out = np.concatenate([self.slots[r] for r in range(self.world)])
+        self.bar.wait()
+        return out
+
+
+@pytest.mark.parametrize("world,n,seed", [(2, 10, 0), (4, 11, 1), (8, 12, 2)])
+def test_sharded_threads_one_gpu(native_lib, world, n, seed):
+    from qibochem_b200.engine import DeviceState
+    from qibochem_b200.sharded import ShardedState
+
+    g = world.bit_length() - 1
+    hf, xs, zs, ang, hx, hz, hc = _inputs(n, seed)
+    states = [DeviceState(n - g) for _ in range(world)]
+    bar = threading.Barrier(world)
+    slots = [None] * world
+    results, errors = [None] * world, []
+
+    def run(rank):
+        try:
+            st = ShardedState(n, rank, world, states[rank], ThreadExchanger(rank, world, states, bar, slots))
+            st.set_basis_state(hf)
+            st.apply_pauli_rotations(xs, zs, ang, lookahead=8)
+            e = st.expectation(hx, hz, hc)
+            full = st.gather_logical()
+            st.apply_pauli_rotations(xs[:10], zs[:10], ang[:10])
+            e2 = st.expectation(hx, hz, hc)
+            results[rank] = (e, e2, full, st.n_swaps, st.norm2())
+        except Exception as exc:  # pragma: no cover
+            errors.append(exc)
+            bar.abort()
+
+    threads = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    assert not errors, errors
+    psi = np.zeros(2**n, dtype=complex)
+    psi[hf] = 1
+    for x, z, a in zip(xs.tolist(), zs.tolist(), ang.tolist()):
+        psi = O.apply_pauli_rotation(psi, x, z, a)
+    e_ref = O.expectation_masks(psi, hx.tolist(), hz.tolist(), hc.tolist())
+    psi2 = psi.copy()
+    for x, z, a in zip(xs[:10].tolist(), zs[:10].tolist(), ang[:10].tolist()):
+        psi2 = O.apply_pauli_rotation(psi2, x, z, a)
+    e2_ref = O.expectation_masks(psi2, hx.tolist(), hz.tolist(), hc.tolist())
+    for e, e2, full, swaps, norm in results:
+        assert abs(e - e_ref) < 1e-11 and abs(e2 - e2_ref) < 1e-11
+        assert np.abs(full - psi).max() < 1e-12
+        assert swaps > 0 and abs(norm - 1) < 1e-12
+    for s in states:
+        s.close()
+
+
+def test_sharded_processes_two_gpus(native_lib):
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(ROOT, "tests", "sharded_gpu_worker.py")]  # fmt: skip
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert "SHARDED_OK" in out.stdout
