@@ -67,6 +67,9 @@ int qc_apply_pauli_rotations(qc_state* h, size_t R, const uint64_t* xmask, const
  * Terms are grouped by x-mask; every group costs one read-only sweep of the shard. n_sweeps_out may be NULL. */
 int qc_expectation(qc_state* h, size_t T, const uint64_t* xmask, const uint64_t* zmask, const double* coeff,
                    double* energy_out, double* per_term, int* n_sweeps_out);
+/* Options: "k2_mode" = 0 auto (default), 1 one HBM sweep per x-mask, 2 shared-memory tiles serving many x-masks per
+ * HBM read (needs >= 12 local qubits; falls back to sweeps for x-masks that do not fit a tile). */
+int qc_set_option(qc_state* h, const char* key, int64_t value);
 /* <psi|psi> over this shard. */
 int qc_norm2(qc_state* h, double* out);
 
@@ -93,7 +96,7 @@ int qc_frequencies(qc_state* h, const uint64_t* samples, size_t n, int on_device
 
 /* ---- live profiler / launch counter (bench.py: roofline of the dominant kernel, gpu_launches) ----------------- */
 /* Kernel classes: 0 K0 init, 1 K1 rotation pass, 2 K2 expectation sweeps, 3 reductions, 4 K5 sampling, 5 K3 shot
- * statistics, 6 K4 exchange.  Launch counts and algorithmic bytes are always accumulated; when enabled, every
+ * statistics, 6 K4 exchange, 7 K2 tiled expectation passes.  Launch counts and algorithmic bytes are always accumulated; when enabled, every
  * launch is additionally bracketed by CUDA events on the handle's stream and its device time accumulated. */
 int qc_profile_enable(qc_state* h, int enabled);
 int qc_profile_reset(qc_state* h);

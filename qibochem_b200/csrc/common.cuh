@@ -41,7 +41,10 @@ struct Arena {
 };
 
 // Kernel classes for the launch counter / live profiler (qc_profile_*)
-enum KernelClass { kK0Init = 0, kK1Rotation = 1, kK2Expectation = 2, kReduce = 3, kK5Sampling = 4, kK3Shots = 5, kK4Exchange = 6, kNumClasses = 7 };
+enum KernelClass { kK0Init = 0, kK1Rotation = 1, kK2Expectation = 2, kReduce = 3, kK5Sampling = 4, kK3Shots = 5, kK4Exchange = 6, kK2Tiled = 7, kNumClasses = 8 };
+
+struct TiledPlan;  // expectation_tiled.cu
+void free_tiled_plan(TiledPlan* p);
 
 struct Profiler {
     bool enabled = false;
@@ -80,6 +83,8 @@ struct qc_state {
     double* h_out = nullptr;       // pinned mirror of d_out
     double2* scratch_psi = nullptr;  // scratch copy of the shard (sampling), allocated lazily
     qc::Profiler prof;
+    qc::TiledPlan* k2plan = nullptr;  // cached plan of the tiled expectation (keyed by a hash of the term list)
+    int k2_mode = 0;                  // 0 auto, 1 force sweeps (one HBM pass per x-mask), 2 force tiles
     int ensure_partials(size_t doubles);
     int ensure_out(size_t doubles);
 };

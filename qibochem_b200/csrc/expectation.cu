@@ -134,21 +134,9 @@ __global__ void __launch_bounds__(kThreads) expectation_kernel(const double2* __
     if (threadIdx.x == 0) partials[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = t;
 }
 
-}  // namespace qc
-
-extern "C" int qc_expectation(qc_state* h, size_t T, const uint64_t* xmask, const uint64_t* zmask, const double* coeff,
-                              double* energy_out, double* per_term, int* n_sweeps_out) {
-    using namespace qc;
-    QC_REQUIRE(h && energy_out, "qc_expectation: null argument");
-    *energy_out = 0.0;
-    if (n_sweeps_out) *n_sweeps_out = 0;
-    if (T == 0) return 0;
-    QC_REQUIRE(xmask && zmask && coeff, "qc_expectation: null array");
-    QC_REQUIRE(T < (1ull << 31), "qc_expectation: too many terms");
-    for (size_t k = 0; k < T; ++k)
-        QC_REQUIRE(xmask[k] < h->dim && zmask[k] < h->dim, "qc_expectation: mask has bits outside the shard");
-    QC_CHECK(cudaSetDevice(h->device));
-
+// Sweep path: one launch row per x-group.  Total -> h->d_out[out_slot]; per-group values -> h->d_out[out_slot+1 ...].
+static int run_sweeps(qc_state* h, size_t T, const uint64_t* xmask, const uint64_t* zmask, const double* coeff,
+                      bool per_term, size_t out_slot, size_t* ng_out) {
     // ---- group the terms by x-mask (stable), even-nY terms first inside a group
     std::vector<uint32_t> order(T);
     std::iota(order.begin(), order.end(), 0u);
@@ -200,7 +188,7 @@ extern "C" int qc_expectation(qc_state* h, size_t T, const uint64_t* xmask, cons
 
     const int nbx = grid_for(h->dim >> 1, 4, h->sm_count);
     const size_t chunk = std::min(ng, (size_t)kMaxGroupsPerLaunch);
-    if (h->ensure_partials(chunk * nbx) || h->ensure_out(ng + 1)) return 1;
+    if (h->ensure_partials(chunk * nbx) || h->ensure_out(out_slot + ng + 1)) return 1;
     for (size_t g0 = 0; g0 < ng; g0 += chunk) {
         const size_t gn = std::min(chunk, ng - g0);
         dim3 grid(nbx, (unsigned)gn);
@@ -209,8 +197,52 @@ extern "C" int qc_expectation(qc_state* h, size_t T, const uint64_t* xmask, cons
             expectation_kernel<4><<<grid, kThreads, 0, h->stream>>>(h->psi, h->dim, dgroups + g0, dterms, h->d_partials);
         }
         QC_CHECK(cudaGetLastError());
-        if (fold_partials(h, h->d_partials, (int)gn, nbx, nbx, h->d_out + 1 + g0)) return 1;
+        if (fold_partials(h, h->d_partials, (int)gn, nbx, nbx, h->d_out + out_slot + 1 + g0)) return 1;
     }
+    if (!per_term)
+        if (fold_partials(h, h->d_out + out_slot + 1, 1, (int)ng, (int)ng, h->d_out + out_slot)) return 1;
+    *ng_out = ng;
+    return 0;
+}
+
+int run_tiled_expectation(qc_state* h, size_t T, const uint64_t* xs, const uint64_t* zs, const double* cs, int out_slot,
+                          int* n_passes_out, const TiledPlan** plan_out);
+void tiled_plan_leftovers(const TiledPlan* plan, const uint64_t** x, const uint64_t** z, const double** c, size_t* count);
+
+}  // namespace qc
+
+extern "C" int qc_expectation(qc_state* h, size_t T, const uint64_t* xmask, const uint64_t* zmask, const double* coeff,
+                              double* energy_out, double* per_term, int* n_sweeps_out) {
+    using namespace qc;
+    QC_REQUIRE(h && energy_out, "qc_expectation: null argument");
+    *energy_out = 0.0;
+    if (n_sweeps_out) *n_sweeps_out = 0;
+    if (T == 0) return 0;
+    QC_REQUIRE(xmask && zmask && coeff, "qc_expectation: null array");
+    QC_REQUIRE(T < (1ull << 31), "qc_expectation: too many terms");
+    for (size_t k = 0; k < T; ++k)
+        QC_REQUIRE(xmask[k] < h->dim && zmask[k] < h->dim, "qc_expectation: mask has bits outside the shard");
+    QC_CHECK(cudaSetDevice(h->device));
+
+    const bool tiled = !per_term && h->n >= 12 && (h->k2_mode == 2 || (h->k2_mode == 0 && h->n >= 16 && T >= 512));
+    if (tiled) {
+        int passes = 0;
+        const TiledPlan* plan = nullptr;
+        if (run_tiled_expectation(h, T, xmask, zmask, coeff, 0, &passes, &plan)) return 1;
+        const uint64_t *lx, *lz;
+        const double* lc;
+        size_t nleft = 0, ng = 0;
+        tiled_plan_leftovers(plan, &lx, &lz, &lc, &nleft);
+        if (nleft && run_sweeps(h, nleft, lx, lz, lc, false, 1, &ng)) return 1;
+        QC_CHECK(cudaMemcpyAsync(h->h_out, h->d_out, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        QC_CHECK(cudaStreamSynchronize(h->stream));
+        *energy_out = h->h_out[0] + (nleft ? h->h_out[1] : 0.0);
+        if (n_sweeps_out) *n_sweeps_out = passes + (int)ng;
+        return 0;
+    }
+
+    size_t ng = 0;
+    if (run_sweeps(h, T, xmask, zmask, coeff, per_term != nullptr, 0, &ng)) return 1;
     if (per_term) {
         QC_CHECK(cudaMemcpyAsync(h->h_out, h->d_out, (ng + 1) * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         QC_CHECK(cudaStreamSynchronize(h->stream));
@@ -221,7 +253,6 @@ extern "C" int qc_expectation(qc_state* h, size_t T, const uint64_t* xmask, cons
         }
         *energy_out = e;
     } else {
-        if (fold_partials(h, h->d_out + 1, 1, (int)ng, (int)ng, h->d_out)) return 1;
         QC_CHECK(cudaMemcpyAsync(h->h_out, h->d_out, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         QC_CHECK(cudaStreamSynchronize(h->stream));
         *energy_out = h->h_out[0];

@@ -1,4 +1,6 @@
 // State life cycle, K0 (basis state), host<->device copies, norm.
+#include <string.h>
+
 #include "common.cuh"
 
 namespace qc {
@@ -168,6 +170,7 @@ int qc_destroy(qc_state* h) {
     if (h->h_out) cudaFreeHost(h->h_out);
     h->arena.release();
     h->prof.release();
+    qc::free_tiled_plan(h->k2plan);
     if (h->owns_stream) cudaStreamDestroy(h->stream);
     delete h;
     return 0;
@@ -216,6 +219,17 @@ int qc_norm2(qc_state* h, double* out) {
     QC_CHECK(cudaStreamSynchronize(h->stream));
     *out = h->h_out[0];
     return 0;
+}
+
+int qc_set_option(qc_state* h, const char* key, int64_t value) {
+    QC_REQUIRE(h && key, "qc_set_option: null argument");
+    if (strcmp(key, "k2_mode") == 0) {
+        QC_REQUIRE(value >= 0 && value <= 2, "qc_set_option: k2_mode must be 0 (auto), 1 (sweeps) or 2 (tiles)");
+        h->k2_mode = (int)value;
+        return 0;
+    }
+    qc::set_error(std::string("qc_set_option: unknown key ") + key);
+    return 2;
 }
 
 int qc_profile_enable(qc_state* h, int enabled) {

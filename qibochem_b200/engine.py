@@ -211,7 +211,11 @@ class DeviceState:
         )  # fmt: skip
 
     # -- profiler ----------------------------------------------------------------------------------------------
-    KERNEL_CLASSES = ("k0_init", "k1_rotation", "k2_expectation", "reduce", "k5_sampling", "k3_shots", "k4_exchange")
+    KERNEL_CLASSES = ("k0_init", "k1_rotation", "k2_expectation", "reduce", "k5_sampling", "k3_shots", "k4_exchange", "k2_tiled")
+
+    def set_option(self, key: str, value: int) -> None:
+        """e.g. ``set_option("k2_mode", 1)``: 0 auto, 1 sweeps (one HBM pass per x-mask), 2 tiles."""
+        _native.check(self._lib.qc_set_option(self._h, key.encode(), int(value)), "qc_set_option")
 
     def profile_enable(self, enabled: bool = True) -> None:
         _native.check(self._lib.qc_profile_enable(self._h, int(enabled)), "qc_profile_enable")
