@@ -70,6 +70,13 @@ int qc_expectation(qc_state* h, size_t T, const uint64_t* xmask, const uint64_t*
 /* Options: "k2_mode" = 0 auto (default), 1 one HBM sweep per x-mask, 2 shared-memory tiles serving many x-masks per
  * HBM read (needs >= 12 local qubits; falls back to sweeps for x-masks that do not fit a tile). */
 int qc_set_option(qc_state* h, const char* key, int64_t value);
+/* Host-only (no GPU needed): plans the tiled expectation of a term list and reports its shape.  stats_out: 16 x
+ * uint64 {x-masks, tiled x-masks, HBM passes, register sub-cubes, DOT records, LIN entries, leftover terms (sweep
+ * kernel), record units, then the number of sub-cubes holding 0,1,..,>=7 x-masks}.  check_out (may be NULL) receives
+ * the planner self-check: max |W_plan - W_direct| over random (x-mask, index) samples of the per-pair weights
+ * W_x(i) = sum_k d_k (-1)^{popcount(i & z_k)}; negative if some x-mask is not served exactly once. */
+int qc_k2_plan_stats(int n_local_qubits, size_t T, const uint64_t* xmask, const uint64_t* zmask, const double* coeff,
+                     uint64_t* stats_out, double* check_out);
 /* <psi|psi> over this shard. */
 int qc_norm2(qc_state* h, double* out);
 

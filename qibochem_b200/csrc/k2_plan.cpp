@@ -1,0 +1,669 @@
+// Host-side planner of the tiled expectation (K2T).  See k2_plan.h for the data it produces and
+// expectation_tiled.cu for the kernel that consumes it.
+//
+// Cost model behind the heuristics (B200, per SM): a sub-cube gather moves the whole 64 KB tile through shared
+// memory once (512 clk at 128 B/clk); an x-mask evaluated from registers costs 48 DFMA per thread (~96 clk of the
+// FP64 pipe per tile).  So the planner (1) packs as many x-masks as it can into every 5-bit sub-cube R, and (2) lets
+// the x-masks that would sit alone in a sub-cube wait for a later pass where they may find company.
+#include "k2_plan.h"
+
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <numeric>
+#include <unordered_map>
+
+namespace qc {
+namespace {
+
+inline int popc64(uint64_t v) { return __builtin_popcountll(v); }
+inline int popc32(uint32_t v) { return __builtin_popcount(v); }
+
+int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+
+struct XG {  // terms of one x-mask
+    uint64_t x;
+    std::vector<uint32_t> terms;
+    float weight;  // rough evaluation cost in units of one 4-term group
+};
+
+struct Term {  // one term seen from inside a sub-cube
+    uint64_t z_not_r;
+    uint32_t pk;  // z on the sub-cube bits (pair groups: highest x bit cleared)
+    int odd;
+    double d;
+};
+
+uint32_t compress_bits(uint64_t mask, const int* pos, int count) {
+    uint32_t out = 0;
+    for (int j = 0; j < count; ++j)
+        if ((mask >> pos[j]) & 1ull) out |= 1u << j;
+    return out;
+}
+
+void push_units(std::vector<Unit16>& recs, const void* data, size_t bytes) {
+    const size_t units = bytes / 16;
+    const size_t at = recs.size();
+    recs.resize(at + units);
+    memcpy(recs.data() + at, data, bytes);
+}
+
+// sign pattern of z-bits `pk` over the 16 canonical pair indices (x != 0) or over one half of the cube (diagonal)
+void pattern_table(uint32_t xr, uint32_t pk, int half, double scale, double* tab /*16*/) {
+    if (xr == 0) {
+        for (int k = 0; k < 16; ++k) tab[k] = (popc32((uint32_t)(k + 16 * half) & pk) & 1) ? -scale : scale;
+        return;
+    }
+    const int hb = 31 - __builtin_clz(xr);
+    int kk = 0;
+    for (int p = 0; p < 32; ++p) {
+        if ((p >> hb) & 1) continue;
+        tab[kk++] = (popc32((uint32_t)p & pk) & 1) ? -scale : scale;
+    }
+}
+
+struct DotRec {
+    TRecHdr h;
+    double tab[16];
+};
+struct LinEntry {
+    uint64_t z_outer;
+    uint32_t z_rest;
+    uint32_t pad;
+    double c[kSlots];
+};
+static_assert(sizeof(DotRec) == 16 * kDotUnits, "record layout");
+static_assert(sizeof(LinEntry) == 16 * kLinEntryUnits, "record layout");
+
+// Records of one x-group inside one sub-cube, as ATOMS that may be placed in different passes (a pass's blob is
+// capped): `setup` (the SET/ADD records forming the pattern sums A[slot]) must precede, inside the same sub-cube
+// visit, every atom with needs_setup.
+struct Atom {
+    std::vector<Unit16> units;
+    uint32_t n_recs = 0;
+    bool needs_setup = false;
+};
+struct GroupRecs {
+    std::vector<Unit16> setup;
+    uint32_t setup_recs = 0;
+    std::vector<Atom> atoms;
+};
+constexpr size_t kLinChunk = 200;  // LIN entries per record
+
+GroupRecs emit_group(const XG& g, const uint64_t* zs, const double* cs, uint64_t S, const int* spos, uint64_t r_global,
+                     const int* rglob /*global positions of the R bits*/, PlanStats& st) {
+    GroupRecs out;
+    const uint32_t xr = compress_bits(g.x, rglob, kRBits);
+    const uint32_t hbbit = xr ? (1u << (31 - __builtin_clz(xr))) : 0u;
+    const double pair_scale = xr ? 2.0 : 1.0;
+    const int halves = xr ? 1 : 2;
+
+    // ---- subgroups: terms that agree outside the sub-cube (and in parity type)
+    std::map<std::pair<uint64_t, int>, std::vector<Term>> subs;
+    for (uint32_t t : g.terms) {
+        const uint64_t z = zs[t];
+        const int ny = popc64(g.x & z);
+        Term tm;
+        tm.z_not_r = z & ~r_global;
+        tm.pk = compress_bits(z, rglob, kRBits) & ~hbbit;
+        tm.odd = ny & 1;
+        tm.d = cs[t] * (((ny >> 1) & 1) ? -1.0 : 1.0);
+        subs[{tm.z_not_r, tm.odd}].push_back(tm);
+    }
+    // ---- shared sign patterns: worth a slot when >= 3 subgroups use them
+    std::map<std::pair<uint32_t, int>, int> freq;  // (pk, odd) -> number of subgroups containing it
+    for (auto& kv : subs) {
+        std::vector<uint32_t> seen;
+        for (const Term& tm : kv.second)
+            if (std::find(seen.begin(), seen.end(), tm.pk) == seen.end()) seen.push_back(tm.pk);
+        for (uint32_t pk : seen) freq[{pk, kv.first.second}] += 1;
+    }
+    std::vector<std::pair<int, std::pair<uint32_t, int>>> by_freq;
+    for (auto& kv : freq)
+        if (kv.second >= 3) by_freq.push_back({kv.second, kv.first});
+    std::stable_sort(by_freq.begin(), by_freq.end(), [](const auto& a, const auto& b) { return a.first > b.first; });
+    if (by_freq.size() > (size_t)kSlots) by_freq.resize(kSlots);
+    auto slot_of = [&](uint32_t pk, int odd) -> int {
+        for (size_t j = 0; j < by_freq.size(); ++j)
+            if (by_freq[j].second.first == pk && by_freq[j].second.second == odd) return (int)j;
+        return -1;
+    };
+    std::vector<const std::vector<Term>*> lin_subs, tab_subs;
+    std::vector<std::pair<uint64_t, int>> lin_keys, tab_keys;
+    bool slot_used[kSlots] = {false, false, false, false};
+    for (auto& kv : subs) {
+        bool linear = !by_freq.empty();
+        for (const Term& tm : kv.second)
+            if (slot_of(tm.pk, tm.odd) < 0) linear = false;
+        if (linear) {
+            lin_subs.push_back(&kv.second), lin_keys.push_back(kv.first);
+        } else {
+            tab_subs.push_back(&kv.second), tab_keys.push_back(kv.first);
+        }
+    }
+    if (lin_subs.size() < 3) {  // not worth the pattern sums
+        for (size_t i = 0; i < lin_subs.size(); ++i) tab_subs.push_back(lin_subs[i]), tab_keys.push_back(lin_keys[i]);
+        lin_subs.clear(), lin_keys.clear();
+    }
+    for (const auto* sub : lin_subs)
+        for (const Term& tm : *sub) slot_used[slot_of(tm.pk, tm.odd)] = true;
+
+    auto header = [&](uint64_t z_not_r, uint32_t meta) {
+        TRecHdr h;
+        h.z_outer = z_not_r & ~S;
+        h.z_rest = compress_bits(z_not_r & S, spos, kTileBits);
+        h.meta = meta;
+        return h;
+    };
+    // ---- pattern sums A[slot]
+    if (!lin_subs.empty()) {
+        for (size_t j = 0; j < by_freq.size(); ++j) {
+            if (!slot_used[j]) continue;
+            const uint32_t pk = by_freq[j].second.first;
+            const int odd = by_freq[j].second.second;
+            for (int half = 0; half < halves; ++half) {
+                DotRec r;
+                const uint32_t kind = xr ? kRecDot : (half ? kRecDiagHi : kRecDiagLo);
+                r.h = header(0, rec_meta(xr, (uint32_t)odd, kind, half ? kModeAdd : kModeSet, (uint32_t)j, 0));
+                pattern_table(xr, pk, half, pair_scale, r.tab);
+                push_units(out.setup, &r, sizeof(r));
+                ++out.setup_recs;
+            }
+        }
+        for (size_t done = 0; done < lin_subs.size(); done += kLinChunk) {
+            const size_t cnt = std::min(lin_subs.size() - done, kLinChunk);
+            Atom atom;
+            atom.needs_setup = true;
+            atom.n_recs = 1;
+            TRecHdr h = header(0, rec_meta(xr, 0, kRecLin, kModeAcc, 0, (uint32_t)cnt));
+            push_units(atom.units, &h, sizeof(h));
+            for (size_t i = done; i < done + cnt; ++i) {
+                LinEntry e;
+                memset(&e, 0, sizeof(e));
+                const TRecHdr eh = header(lin_keys[i].first, 0);
+                e.z_outer = eh.z_outer;
+                e.z_rest = eh.z_rest;
+                for (const Term& tm : *lin_subs[i]) e.c[slot_of(tm.pk, tm.odd)] += tm.d;
+                push_units(atom.units, &e, sizeof(e));
+                ++st.n_lin;
+            }
+            out.atoms.push_back(std::move(atom));
+        }
+    }
+    // ---- subgroups with their own weight table
+    for (size_t i = 0; i < tab_subs.size(); ++i) {
+        Atom atom;
+        for (int half = 0; half < halves; ++half) {
+            DotRec r;
+            const uint32_t kind = xr ? kRecDot : (half ? kRecDiagHi : kRecDiagLo);
+            r.h = header(tab_keys[i].first, rec_meta(xr, (uint32_t)tab_keys[i].second, kind, kModeAcc, 0, 0));
+            for (int k = 0; k < 16; ++k) r.tab[k] = 0.0;
+            double pat[16];
+            for (const Term& tm : *tab_subs[i]) {
+                pattern_table(xr, tm.pk, half, pair_scale * tm.d, pat);
+                for (int k = 0; k < 16; ++k) r.tab[k] += pat[k];
+            }
+            push_units(atom.units, &r, sizeof(r));
+            ++atom.n_recs;
+        }
+        out.atoms.push_back(std::move(atom));
+    }
+    return out;
+}
+
+// All kRBits-subsets of the kTileBits tile-local positions.  `conflict_free` marks those that leave, outside the
+// sub-cube, positions of all three residues mod 3: only then can the lanes of a quarter warp be mapped to distinct
+// shared-memory bank groups (the others still work, with 2-way conflicts on the gather, and are used as a last resort).
+struct CubeCands {
+    std::vector<uint32_t> mask;
+    std::vector<char> conflict_free;
+};
+const CubeCands& cube_candidates() {
+    static CubeCands cc;
+    if (cc.mask.empty()) {
+        for (uint32_t m = 0; m < (1u << kTileBits); ++m) {
+            if (popc32(m) != kRBits) continue;
+            bool ok = true;
+            for (int res = 0; res < 3; ++res) {
+                bool any = false;
+                for (int b = res; b < kTileBits; b += 3)
+                    if (!((m >> b) & 1u)) any = true;
+                ok = ok && any;
+            }
+            cc.mask.push_back(m);
+            cc.conflict_free.push_back(ok ? 1 : 0);
+        }
+    }
+    return cc;
+}
+
+}  // namespace
+
+HostPlan* build_host_plan(int n, size_t T, const uint64_t* xs, const uint64_t* zs, const double* cs) {
+    HostPlan* plan = new HostPlan();
+    plan->n = n;
+    PlanStats& st = plan->stats;
+    const int tau0 = env_int("QC_K2_TAU", 3);            // first passes only build sub-cubes of >= tau x-masks
+    const int min_gain = env_int("QC_K2_MIN_GAIN", 48);  // ... until a pass would serve fewer x-masks than this
+
+    // ---- x-groups
+    std::vector<XG> xg;
+    {
+        std::unordered_map<uint64_t, uint32_t> index;
+        index.reserve(T / 2 + 16);
+        for (size_t k = 0; k < T; ++k) {
+            auto it = index.find(xs[k]);
+            if (it == index.end()) {
+                index.emplace(xs[k], (uint32_t)xg.size());
+                xg.push_back({xs[k], {}, 1.0f});
+                xg.back().terms.push_back((uint32_t)k);
+            } else {
+                xg[it->second].terms.push_back((uint32_t)k);
+            }
+        }
+    }
+    st.n_groups = xg.size();
+    std::vector<uint32_t> uncovered;
+    int diag_group = -1;
+    for (uint32_t g = 0; g < xg.size(); ++g) {
+        const uint64_t x = xg[g].x;
+        xg[g].weight = xg[g].terms.size() <= 8 ? 1.0f : 4.0f;
+        if (x == 0) {
+            diag_group = (int)g;
+        } else if (popc64(x) <= kRBits && popc64(x | 1ull) <= kTileBits) {
+            uncovered.push_back(g);
+        } else {
+            for (uint32_t t : xg[g].terms) {
+                plan->left_x.push_back(xs[t]);
+                plan->left_z.push_back(zs[t]);
+                plan->left_c.push_back(cs[t]);
+            }
+        }
+    }
+    st.n_leftover_terms = plan->left_x.size();
+    st.n_tiled_groups = uncovered.size() + (diag_group >= 0 ? 1 : 0);
+
+    const CubeCands& cube_cands = cube_candidates();
+    const std::vector<uint32_t>& cands = cube_cands.mask;
+    const int free_slots = kTileBits - 1;
+    bool diag_pending = diag_group >= 0;
+    int tau = std::max(1, tau0);
+
+    while (!uncovered.empty() || diag_pending) {
+        // ---- tile bits S: greedy, one bit at a time, scored by how close it brings the uncovered x-masks to fitting
+        uint64_t S = 1ull;
+        for (int slot = 0; slot < free_slots; ++slot) {
+            const int remaining_after = free_slots - slot - 1;
+            double delta[64] = {0.0};
+            for (uint32_t g : uncovered) {
+                const uint64_t need = xg[g].x & ~S;
+                const int miss = popc64(need);
+                if (miss == 0 || miss - 1 > remaining_after) continue;
+                const double f0 = miss <= remaining_after ? (double)(4096 >> (3 * std::min(miss, 4))) : 0.0;
+                const double f1 = (double)(4096 >> (3 * std::min(miss - 1, 4)));
+                const double dlt = (f1 - f0) * xg[g].weight;
+                uint64_t m = need;
+                while (m) {
+                    delta[__builtin_ctzll(m)] += dlt;
+                    m &= m - 1;
+                }
+            }
+            int best_bit = -1;
+            double best = 0.0;
+            for (int b = 1; b < n; ++b) {
+                if ((S >> b) & 1ull) continue;
+                if (best_bit < 0 || delta[b] > best) best = delta[b], best_bit = b;
+            }
+            S |= 1ull << best_bit;
+        }
+        int spos[kTileBits];
+        {
+            uint64_t m = S;
+            for (int j = 0; j < kTileBits; ++j) {
+                spos[j] = __builtin_ctzll(m);
+                m &= m - 1;
+            }
+        }
+        std::vector<uint32_t> mine, others;
+        for (uint32_t g : uncovered) ((xg[g].x & ~S) == 0 ? mine : others).push_back(g);
+
+        // ---- sub-cubes: greedy cover of this pass's x-masks by 5-bit subsets of the tile bits
+        std::vector<uint32_t> xl(mine.size());
+        for (size_t i = 0; i < mine.size(); ++i) xl[i] = compress_bits(xg[mine[i]].x, spos, kTileBits);
+        std::vector<float> cnt(cands.size(), 0.0f);
+        for (size_t i = 0; i < mine.size(); ++i)
+            for (size_t c = 0; c < cands.size(); ++c)
+                if ((xl[i] & ~cands[c]) == 0) cnt[c] += xg[mine[i]].weight;
+        std::vector<char> assigned(mine.size(), 0);
+        std::vector<std::pair<uint32_t, std::vector<uint32_t>>> cubes;  // (R tile-local, group ids)
+        float total_w = 0.0f;
+        for (;;) {
+            // lower the bar when this pass would otherwise be too thin
+            size_t best_c = 0;
+            float best = -1.0f;
+            for (size_t c = 0; c < cands.size(); ++c) {
+                const float v = cube_cands.conflict_free[c] ? cnt[c] : 0.5f * cnt[c];
+                if (v > best) best = v, best_c = c;
+            }
+            if (best <= 0.0f) break;
+            best = cnt[best_c];
+            if (best < (float)tau) {
+                if (total_w >= (float)min_gain || tau == 1) break;
+                --tau;
+                continue;
+            }
+            const uint32_t R = cands[best_c];
+            std::vector<uint32_t> members;
+            for (size_t i = 0; i < mine.size(); ++i) {
+                if (assigned[i] || (xl[i] & ~R) != 0) continue;
+                assigned[i] = 1;
+                members.push_back(mine[i]);
+                total_w += xg[mine[i]].weight;
+                for (size_t c = 0; c < cands.size(); ++c)
+                    if ((xl[i] & ~cands[c]) == 0) cnt[c] -= xg[mine[i]].weight;
+            }
+            cnt[best_c] = 0.0f;
+            cubes.push_back({R, members});
+        }
+        for (size_t i = 0; i < mine.size(); ++i)
+            if (!assigned[i]) others.push_back(mine[i]);
+        if (cubes.empty() && !diag_pending) {
+            // cannot happen (tau reaches 1 and every tileable x-mask fits some candidate); guard against looping
+            for (uint32_t g : others)
+                for (uint32_t t : xg[g].terms) {
+                    plan->left_x.push_back(xs[t]);
+                    plan->left_z.push_back(zs[t]);
+                    plan->left_c.push_back(cs[t]);
+                }
+            st.n_leftover_terms = plan->left_x.size();
+            others.clear();
+            uncovered.clear();
+            break;
+        }
+        uncovered.swap(others);
+        if (diag_pending) {
+            if (cubes.empty()) cubes.push_back({cands[0], {}});
+            cubes[0].second.push_back((uint32_t)diag_group);
+            diag_pending = false;
+        }
+
+        // ---- emit the pass (split into several passes over the same S when its blob would exceed the cap)
+        struct RB {
+            TRBlock hdr;
+            std::vector<Unit16> recs;
+        };
+        std::vector<RB> cur;       // sub-cube visits of the pass being assembled
+        uint32_t cur_units = 0;    // headers + records
+        uint32_t cur_groups = 0;
+        auto flush_pass = [&]() {
+            if (cur.empty()) return;
+            TPass pass;
+            memset(&pass, 0, sizeof(pass));
+            pass.s_mask = S;
+            for (int j = 0; j < kTileBits; ++j) pass.spos[j] = (uint8_t)spos[j];
+            pass.blob_off = (uint32_t)plan->units.size();
+            pass.n_rblocks = (uint32_t)cur.size();
+            pass.n_groups = cur_groups;
+            uint32_t rec_off = (uint32_t)cur.size() * kRBlockUnits;
+            for (RB& rb : cur) {
+                rb.hdr.rec_off = rec_off;
+                rec_off += (uint32_t)rb.recs.size();
+                push_units(plan->units, &rb.hdr, sizeof(TRBlock));
+            }
+            for (RB& rb : cur) plan->units.insert(plan->units.end(), rb.recs.begin(), rb.recs.end());
+            pass.blob_units = rec_off;
+            plan->passes.push_back(pass);
+            st.n_rblocks += cur.size();
+            cur.clear();
+            cur_units = 0, cur_groups = 0;
+        };
+        for (auto& cube : cubes) {
+            const uint32_t R = cube.first;
+            int rpos[kRBits], rglob[kRBits];
+            {
+                uint32_t m = R;
+                for (int j = 0; j < kRBits; ++j) {
+                    rpos[j] = __builtin_ctz(m);
+                    rglob[j] = spos[rpos[j]];
+                    m &= m - 1;
+                }
+            }
+            uint64_t r_global = 0;
+            for (int j = 0; j < kRBits; ++j) r_global |= 1ull << rglob[j];
+            TRBlock blk;
+            memset(&blk, 0, sizeof(blk));
+            for (int j = 0; j < kRBits; ++j) blk.sbit[j] = (uint16_t)k2_swizzle(1u << rpos[j]);
+            // thread bit -> tile position outside the cube; the three lowest thread bits get positions with distinct
+            // residues mod 3 (distinct swizzle columns => conflict-free 128-bit shared loads inside a quarter warp)
+            {
+                std::vector<int> rest_pos, perm;
+                for (int b = 0; b < kTileBits; ++b)
+                    if (!((R >> b) & 1u)) rest_pos.push_back(b);
+                std::vector<char> used(rest_pos.size(), 0);
+                for (int res = 0; res < 3; ++res)
+                    for (size_t i = 0; i < rest_pos.size(); ++i)
+                        if (!used[i] && rest_pos[i] % 3 == res) {
+                            perm.push_back(rest_pos[i]);
+                            used[i] = 1;
+                            break;
+                        }
+                for (size_t i = 0; i < rest_pos.size(); ++i)
+                    if (!used[i]) perm.push_back(rest_pos[i]);
+                for (size_t j = 0; j < perm.size(); ++j) blk.perm[j] = (uint8_t)perm[j];
+            }
+            // groups sorted by their in-cube mask: consecutive records then take the same branch of the kernel
+            std::vector<uint32_t> members = cube.second;
+            std::stable_sort(members.begin(), members.end(), [&](uint32_t a, uint32_t b) {
+                return compress_bits(xg[a].x, rglob, kRBits) < compress_bits(xg[b].x, rglob, kRBits);
+            });
+            bool open = false;  // a visit of this sub-cube is open in `cur`
+            uint32_t visit_groups = 0;
+            auto open_visit = [&]() {
+                cur.push_back({blk, {}});
+                cur_units += kRBlockUnits;
+                open = true;
+                visit_groups = 0;
+            };
+            auto close_visit = [&]() {
+                if (open) st.rblock_hist[std::min<uint32_t>(visit_groups, 7)] += 1;
+                open = false;
+            };
+            for (uint32_t g : members) {
+                GroupRecs gr = emit_group(xg[g], zs, cs, S, spos, r_global, rglob, st);
+                bool setup_here = false, counted = false;
+                for (Atom& atom : gr.atoms) {
+                    const bool want_setup = atom.needs_setup && !setup_here;
+                    const uint32_t need = (uint32_t)atom.units.size() + (want_setup ? (uint32_t)gr.setup.size() : 0u) +
+                                          (open ? 0u : kRBlockUnits);
+                    if (cur_units + need > kBlobCapUnits) {
+                        close_visit();
+                        flush_pass();
+                        setup_here = false;
+                    }
+                    if (!open) open_visit();
+                    RB& rb = cur.back();
+                    if (atom.needs_setup && !setup_here) {
+                        rb.recs.insert(rb.recs.end(), gr.setup.begin(), gr.setup.end());
+                        rb.hdr.n_recs += gr.setup_recs;
+                        cur_units += (uint32_t)gr.setup.size();
+                        st.n_dot += gr.setup_recs;
+                        setup_here = true;
+                    }
+                    rb.recs.insert(rb.recs.end(), atom.units.begin(), atom.units.end());
+                    rb.hdr.n_recs += atom.n_recs;
+                    cur_units += (uint32_t)atom.units.size();
+                    if (!atom.needs_setup) st.n_dot += atom.n_recs;
+                    if (!counted) {
+                        counted = true;
+                        rb.hdr.n_groups += 1, ++visit_groups, ++cur_groups;
+                    }
+                }
+            }
+            close_visit();
+        }
+        flush_pass();
+    }
+    st.n_passes = plan->passes.size();
+    return plan;
+}
+
+double check_host_plan(const HostPlan* plan, size_t T, const uint64_t* xs, const uint64_t* zs, const double* cs,
+                       size_t samples, uint64_t seed) {
+    // index: x-mask -> record segments (pass, sub-cube visit, first unit, unit count), in execution order
+    struct Where {
+        uint32_t pass, rblock_unit, first, units;
+    };
+    auto cube_bits = [](const TPass& pass, const TRBlock& blk, int* rglob) {
+        for (int j = 0; j < kRBits; ++j) {
+            rglob[j] = -1;
+            for (int b = 0; b < kTileBits; ++b)
+                if (k2_swizzle(1u << b) == blk.sbit[j]) rglob[j] = pass.spos[b];
+            if (rglob[j] < 0) return false;
+        }
+        return true;
+    };
+    std::unordered_map<uint64_t, std::vector<Where>> where;
+    for (uint32_t p = 0; p < plan->passes.size(); ++p) {
+        const TPass& pass = plan->passes[p];
+        if (pass.blob_units > kBlobCapUnits) return -1.0;
+        for (uint32_t rb = 0; rb < pass.n_rblocks; ++rb) {
+            TRBlock blk;
+            const uint32_t hdr_unit = pass.blob_off + rb * kRBlockUnits;
+            memcpy(&blk, &plan->units[hdr_unit], sizeof(blk));
+            int rglob[kRBits];
+            if (!cube_bits(pass, blk, rglob)) return -1.0;
+            // the thread -> origin map must be a bijection onto the tile positions outside the cube
+            uint32_t seen = 0;
+            for (int j = 0; j < kTileBits - kRBits; ++j) seen |= 1u << blk.perm[j];
+            for (int j = 0; j < kRBits; ++j)
+                for (int b = 0; b < kTileBits; ++b)
+                    if (k2_swizzle(1u << b) == blk.sbit[j]) seen |= 1u << b;
+            if (seen != (1u << kTileBits) - 1u) return -1.0;
+            uint32_t u = pass.blob_off + blk.rec_off;
+            for (uint32_t r = 0; r < blk.n_recs; ++r) {
+                TRecHdr h;
+                memcpy(&h, &plan->units[u], sizeof(h));
+                const uint32_t units = meta_kind(h.meta) == kRecLin ? 1 + kLinEntryUnits * meta_count(h.meta) : kDotUnits;
+                uint64_t x = 0;
+                for (int j = 0; j < kRBits; ++j)
+                    if ((meta_xr(h.meta) >> j) & 1u) x |= 1ull << rglob[j];
+                auto& v = where[x];
+                if (!v.empty() && v.back().rblock_unit == hdr_unit && v.back().first + v.back().units == u)
+                    v.back().units += units;
+                else
+                    v.push_back({p, hdr_unit, u, units});
+                u += units;
+            }
+            if (u > pass.blob_off + pass.blob_units) return -1.0;
+        }
+    }
+    // term groups
+    std::unordered_map<uint64_t, std::vector<uint32_t>> groups;
+    for (size_t k = 0; k < T; ++k) groups[xs[k]].push_back((uint32_t)k);
+    std::vector<uint64_t> keys;
+    for (auto& kv : groups) keys.push_back(kv.first);
+    std::sort(keys.begin(), keys.end());
+    std::unordered_map<uint64_t, char> is_left;
+    for (uint64_t x : plan->left_x) is_left[x] = 1;
+    for (uint64_t x : keys)
+        if (!is_left.count(x) && !where.count(x)) return -1.0;  // an x-mask nobody serves
+
+    uint64_t rng = seed * 0x9E3779B97F4A7C15ull + 0x1234567ull;
+    auto next = [&]() {
+        rng ^= rng << 13, rng ^= rng >> 7, rng ^= rng << 17;
+        return rng;
+    };
+    double worst = 0.0;
+    for (size_t s = 0; s < samples; ++s) {
+        const uint64_t x = keys[next() % keys.size()];
+        if (is_left.count(x)) {
+            if (where.count(x)) return -1.0;
+            continue;
+        }
+        const uint64_t i_raw = next() & ((1ull << plan->n) - 1ull);
+        double got[2] = {0.0, 0.0}, ref[2] = {0.0, 0.0};
+        uint64_t i_ref = i_raw;
+        bool first_seg = true;
+        for (const Where& w : where[x]) {
+            const TPass& pass = plan->passes[w.pass];
+            TRBlock blk;
+            memcpy(&blk, &plan->units[w.rblock_unit], sizeof(blk));
+            int rglob[kRBits], spos[kTileBits];
+            cube_bits(pass, blk, rglob);
+            for (int j = 0; j < kTileBits; ++j) spos[j] = pass.spos[j];
+            const uint32_t xr = compress_bits(x, rglob, kRBits);
+            uint64_t i = i_raw;
+            int k = -1;  // index of p among the products of a record
+            if (xr) {
+                const int hb = 31 - __builtin_clz(xr);
+                if ((i >> rglob[hb]) & 1ull) i ^= x;  // canonical element of the pair in THIS sub-cube
+                const uint32_t p = compress_bits(i, rglob, kRBits);
+                int kk = 0;
+                for (int q = 0; q < 32; ++q) {
+                    if ((q >> hb) & 1) continue;
+                    if ((uint32_t)q == p) k = kk;
+                    ++kk;
+                }
+            }
+            // every segment must weight the SAME pair: W is invariant under i -> i^x up to the sign (-1)^{nY}, which
+            // only matters for odd-nY (Im) terms; compare per segment against the direct weight at its own i
+            if (first_seg) i_ref = i;
+            const uint32_t p = compress_bits(i, rglob, kRBits);
+            const uint32_t org_local = compress_bits(i, spos, kTileBits);
+            const double flip_im = (i == i_ref) ? 1.0 : -1.0;  // Im q changes sign under i <-> i^x
+            double A[kSlots] = {0, 0, 0, 0};
+            int a_type[kSlots] = {0, 0, 0, 0};
+            uint32_t u = w.first;
+            while (u < w.first + w.units) {
+                TRecHdr h;
+                memcpy(&h, &plan->units[u], sizeof(h));
+                const uint32_t kind = meta_kind(h.meta);
+                if (kind == kRecLin) {
+                    for (uint32_t e = 0; e < meta_count(h.meta); ++e) {
+                        LinEntry le;
+                        memcpy(&le, &plan->units[u + 1 + kLinEntryUnits * e], sizeof(le));
+                        const int par = (popc64(i & le.z_outer) + popc32(org_local & le.z_rest)) & 1;
+                        for (int j = 0; j < kSlots; ++j)
+                            got[a_type[j]] += (par ? -1.0 : 1.0) * le.c[j] * A[j] * (a_type[j] ? flip_im : 1.0);
+                    }
+                    u += 1 + kLinEntryUnits * meta_count(h.meta);
+                    continue;
+                }
+                DotRec r;
+                memcpy(&r, &plan->units[u], sizeof(r));
+                u += kDotUnits;
+                double wgt;
+                if (kind == kRecDot) {
+                    wgt = r.tab[k];
+                } else {
+                    const int half = kind == kRecDiagHi;
+                    wgt = ((int)(p >> 4) == half) ? r.tab[p & 15] : 0.0;
+                }
+                const uint32_t mode = meta_mode(h.meta);
+                if (mode == kModeAcc) {
+                    const int par = (popc64(i & h.z_outer) + popc32(org_local & h.z_rest)) & 1;
+                    got[meta_im(h.meta)] += (par ? -wgt : wgt) * (meta_im(h.meta) ? flip_im : 1.0);
+                } else {
+                    const uint32_t sl = meta_slot(h.meta);
+                    A[sl] = (mode == kModeSet) ? wgt : A[sl] + wgt;
+                    a_type[sl] = (int)meta_im(h.meta);
+                }
+            }
+            first_seg = false;
+        }
+        for (uint32_t t : groups[x]) {
+            const int ny = popc64(x & zs[t]);
+            const double d = cs[t] * (((ny >> 1) & 1) ? -1.0 : 1.0) * (x ? 2.0 : 1.0);
+            ref[ny & 1] += (popc64(i_ref & zs[t]) & 1) ? -d : d;
+        }
+        worst = std::max(worst, std::max(std::abs(got[0] - ref[0]), std::abs(got[1] - ref[1])));
+    }
+    return worst;
+}
+
+}  // namespace qc

@@ -1,0 +1,111 @@
+// Plan of the tiled expectation (K2T): which x-masks are served by which HBM pass / register sub-cube, and the
+// record stream the kernel walks.  Pure host data + the few layout helpers the kernel shares with the planner.
+// The planner (k2_plan.cpp) needs no GPU; expectation_tiled.cu uploads a HostPlan and runs it.
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+
+#include <vector>
+
+#if defined(__CUDACC__)
+#define QC_HD __host__ __device__
+#else
+#define QC_HD
+#endif
+
+namespace qc {
+
+constexpr int kTileBits = 12;                       // amplitudes of one tile: 4096 (64 KB of shared memory)
+constexpr int kTileSize = 1 << kTileBits;
+constexpr int kRBits = 5;                           // register sub-cube: 32 amplitudes per thread
+constexpr int kTileThreads = kTileSize >> kRBits;   // 128
+constexpr int kPairsPerCube = 16;                   // pairs {p, p^x} of a sub-cube
+constexpr int kSlots = 4;                           // pattern sums A[0..3] shared by the LIN entries of a group
+
+// tile-local amplitude index -> shared-memory slot (16-byte units); XORs every 3-bit field into the lowest one so
+// that the 8 lanes of a quarter warp hit 8 distinct 16-byte bank groups for any choice of sub-cube bits
+QC_HD inline uint32_t k2_swizzle(uint32_t t) { return t ^ ((t >> 3) & 7u) ^ ((t >> 6) & 7u) ^ ((t >> 9) & 7u); }
+
+// Per-pass "blob": [TRBlock headers][record stream], staged ONCE per CTA into shared memory next to the tile, so
+// that walking the records costs broadcast LDS instead of dependent global loads.
+constexpr uint32_t kBlobCapUnits = 2816;            // 44 KB of 16-byte units per pass (tile 64 KB + blob: 2 CTAs/SM)
+
+struct TPass {             // kernel parameter (constant bank)
+    uint64_t s_mask;       // the kTileBits index bits of the tile (always contains bit 0)
+    uint8_t spos[kTileBits];  // index-bit position of every tile-local bit, ascending
+    uint32_t blob_off;     // first unit of this pass's blob in the plan's unit array
+    uint32_t blob_units;   // <= kBlobCapUnits
+    uint32_t n_rblocks;
+    uint32_t n_groups;     // x-masks served by this pass
+};
+
+struct TRBlock {           // 32 bytes = 2 units
+    uint16_t sbit[kRBits]; // swizzled tile slot of each sub-cube bit
+    uint8_t perm[kTileBits - kRBits];  // thread-index bit j -> tile-local position outside the sub-cube
+    uint8_t pad[3];
+    uint32_t rec_off;      // first record, in units from the start of the blob
+    uint32_t n_recs;
+    uint32_t n_groups;
+};
+static_assert(sizeof(TRBlock) == 32, "TRBlock layout");
+constexpr uint32_t kRBlockUnits = 2;
+
+// ---- record stream (16-byte units) ----------------------------------------------------------------------------
+// DOT / DIAG record: header + 16 doubles.   w = sum_k tab[k] * prod_k  with
+//     DOT   : prod_k = Re or Im of conj(a_p) a_{p^xr}, p = k-th sub-cube index with the highest bit of xr clear
+//     DIAG_x: prod_k = |a_{k + 16 x}|^2
+//   mode ACC: acc += (-1)^{popc(i & z)} w   (z = header masks, i = thread's index outside the sub-cube)
+//   mode SET / ADD: A[slot] = / += w
+// LIN record: header (count in meta) + count entries of 48 bytes {z_outer, z_rest, pad, c[4]}:
+//     acc += (-1)^{popc(i & z)} (c0 A0 + c1 A1 + c2 A2 + c3 A3)
+struct TRecHdr {
+    uint64_t z_outer;      // z outside the tile (index-bit positions)
+    uint32_t z_rest;       // z on the tile bits outside the sub-cube (tile-local positions)
+    uint32_t meta;
+};
+enum : uint32_t { kRecDot = 0, kRecDiagLo = 1, kRecDiagHi = 2, kRecLin = 3 };
+enum : uint32_t { kModeAcc = 0, kModeSet = 1, kModeAdd = 2 };
+QC_HD inline uint32_t rec_meta(uint32_t xr, uint32_t im, uint32_t kind, uint32_t mode, uint32_t slot, uint32_t count) {
+    return (xr & 31u) | ((im & 1u) << 5) | ((kind & 3u) << 6) | ((mode & 3u) << 8) | ((slot & 3u) << 10) | (count << 16);
+}
+QC_HD inline uint32_t meta_xr(uint32_t m) { return m & 31u; }
+QC_HD inline uint32_t meta_im(uint32_t m) { return (m >> 5) & 1u; }
+QC_HD inline uint32_t meta_kind(uint32_t m) { return (m >> 6) & 3u; }
+QC_HD inline uint32_t meta_mode(uint32_t m) { return (m >> 8) & 3u; }
+QC_HD inline uint32_t meta_slot(uint32_t m) { return (m >> 10) & 3u; }
+QC_HD inline uint32_t meta_count(uint32_t m) { return m >> 16; }
+constexpr uint32_t kDotUnits = 1 + 8;   // header + 16 doubles
+constexpr uint32_t kLinEntryUnits = 3;  // 48 bytes
+
+struct Unit16 {
+    uint64_t lo, hi;
+};
+
+struct PlanStats {
+    uint64_t n_groups = 0;       // distinct x-masks in the term list
+    uint64_t n_tiled_groups = 0; // served by tiles
+    uint64_t n_passes = 0, n_rblocks = 0, n_dot = 0, n_lin = 0, n_leftover_terms = 0;
+    uint64_t rblock_hist[8] = {0};  // R-blocks by number of groups (>= 7 in the last bin)
+};
+
+struct HostPlan {
+    int n = 0;
+    std::vector<TPass> passes;
+    std::vector<Unit16> units;   // all blobs, back to back
+    // terms whose x-mask does not fit a tile / a sub-cube: evaluated by the sweep kernel
+    std::vector<uint64_t> left_x, left_z;
+    std::vector<double> left_c;
+    PlanStats stats;
+};
+
+// Builds the plan for sum_k c_k Re<psi|P_k|psi> on an n-bit shard (n >= kTileBits).  No GPU needed.
+HostPlan* build_host_plan(int n, size_t T, const uint64_t* xs, const uint64_t* zs, const double* cs);
+
+// Planner self-check (tests): for `samples` random (term-group, amplitude index) picks, the weight
+// W_x(i) = sum_{k in group x} d_k (-1)^{popc(i & z_k)} reconstructed from the plan's records vs computed from the
+// term list.  Returns the largest absolute difference (0 when the plan is exact), or -1 if a group is served by
+// no record / more than one sub-cube.
+double check_host_plan(const HostPlan* plan, size_t T, const uint64_t* xs, const uint64_t* zs, const double* cs,
+                       size_t samples, uint64_t seed);
+
+}  // namespace qc

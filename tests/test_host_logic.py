@@ -262,3 +262,40 @@ def test_allocate_shots_edge_cases():
         assert allocate_shots_by_variance(*case["args"]) == case["out"]
     assert allocate_shots_by_variance(120, 20, [0.0, 16.0, 64.0], "vmsa") == [0, 20, 40]
     assert allocate_shots_by_variance(120, 20, [0.0, 16.0, 64.0], "vpsr") == [0, 12, 24]
+
+
+# ---- K2T planner (host only; the GPU parity tests run the plans) -------------------------------------------------
+@pytest.mark.parametrize("n,T", [(12, 400), (14, 1500), (18, 8000), (24, 50000)])
+def test_k2_tiled_plan_serves_every_xmask_once(native_lib, n, T):
+    """The tiled-expectation plan reproduces the per-pair weights W_x(i) = sum_k d_k (-1)^{popc(i & z_k)} of the term
+    list (random samples), serves every x-mask exactly once, and needs far fewer HBM passes than x-masks."""
+    import ctypes as C
+
+    from qibochem_b200 import synthetic
+
+    rng = np.random.default_rng(n)
+    hx, hz, hc, _ = synthetic.molecular_like_hamiltonian(n, T)
+    ex, ez = [], []
+    for w in (1, 1, 2, 3, 3, 5, 5, 6, 7, 4, 4, 2):  # odd-nY terms, odd weights, x-masks too wide for a sub-cube
+        bits = rng.choice(n, size=w, replace=False)
+        x = int(sum(1 << int(b) for b in bits))
+        for _ in range(3):
+            ex.append(x), ez.append(int(rng.integers(0, 2**n)))
+    hx = np.ascontiguousarray(np.concatenate([hx, np.array(ex, dtype=np.uint64)]))
+    hz = np.ascontiguousarray(np.concatenate([hz, np.array(ez, dtype=np.uint64)]))
+    hc = np.ascontiguousarray(np.concatenate([hc, rng.normal(size=len(ex))]))
+    stats = np.zeros(16, dtype=np.uint64)
+    chk = C.c_double(-2.0)
+    u64p, f64p = C.POINTER(C.c_uint64), C.POINTER(C.c_double)
+    rc = native_lib.qc_k2_plan_stats(n, hx.size, hx.ctypes.data_as(u64p), hz.ctypes.data_as(u64p), hc.ctypes.data_as(f64p),
+                                     stats.ctypes.data_as(u64p), C.byref(chk))  # fmt: skip
+    assert rc == 0
+    n_x, n_tiled, n_pass, n_cubes, n_dot, n_lin, n_left = (int(v) for v in stats[:7])
+    assert n_x == np.unique(hx).size
+    assert 0.0 <= chk.value < 1e-12
+    wide = {x for x in ex if bin(x).count("1") > 5}
+    assert n_left == 3 * len(wide)  # only the x-masks wider than a sub-cube go to the sweep kernel
+    assert n_tiled == n_x - len(wide)
+    assert int(stats[8:16].sum()) == n_cubes and n_pass <= n_cubes
+    if T >= 8000:
+        assert n_pass * 20 < n_x and n_tiled / n_cubes > 2.5

@@ -17,8 +17,9 @@ st = DeviceState(n)
 st.set_basis_state(synthetic.hf_index(n, nelec))
 st.apply_pauli_rotations(rx, rz, ra)
 st.profile_enable(True)
+only = sys.argv[3] if len(sys.argv) > 3 else ""
 for mode, name in ((2, "tiles"), (1, "sweeps")):
-    if mode == 1 and n >= 28 and len(sys.argv) <= 3:
+    if (mode == 1 and n >= 28 and only != "all") or (only not in ("", "all") and only != name):
         continue
     st.set_option("k2_mode", mode)
     t0 = time.perf_counter(); e = st.expectation(hx, hz, hc); t1 = time.perf_counter()
