@@ -57,25 +57,35 @@ __device__ __forceinline__ double apply_sign(double v, unsigned par) {
 
 // w = sum_k tab[k] * prod_k over the 16 canonical pairs {p, p^XR} of the sub-cube (p ascending, highest bit of XR
 // clear); prod = Re or Im of conj(a_p) a_{p^XR}.  Everything is static register indexing; 4 independent FMA chains.
+// k-th canonical pair index (p has the highest bit HB of XR clear; ascending)
+template <int HB>
+__device__ __forceinline__ constexpr int pair_index(int k) {
+    return ((k / HB) * 2 * HB) | (k % HB);
+}
+
 template <int XR, bool IM>
 __device__ __forceinline__ double dot_pairs(const double2 (&a)[32], const double2* __restrict__ tab) {
     constexpr int HB = XR >= 16 ? 16 : XR >= 8 ? 8 : XR >= 4 ? 4 : XR >= 2 ? 2 : 1;
-    double2 t[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) t[j] = tab[j];
     double w[4] = {0.0, 0.0, 0.0, 0.0};
+    // two batches of 8 pairs; inside a batch the three dependent steps of a pair are 8 instructions apart
 #pragma unroll
-    for (int p = 0; p < 32; ++p) {
-        if (!(p & HB)) {
-            const int k = ((p / (2 * HB)) * HB) | (p & (HB - 1));  // rank of p among the patterns with bit HB clear
-            double pr;
-            if (IM)
-                pr = a[p].x * a[p ^ XR].y - a[p].y * a[p ^ XR].x;
-            else
-                pr = a[p].x * a[p ^ XR].x + a[p].y * a[p ^ XR].y;
-            const double tk = (k & 1) ? t[k >> 1].y : t[k >> 1].x;
-            w[k & 3] = fma(pr, tk, w[k & 3]);
+    for (int b = 0; b < 2; ++b) {
+        double2 t[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) t[j] = tab[4 * b + j];
+        double pr[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int p = pair_index<HB>(8 * b + j);
+            pr[j] = IM ? a[p].x * a[p ^ XR].y : a[p].x * a[p ^ XR].x;
         }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int p = pair_index<HB>(8 * b + j);
+            pr[j] = IM ? fma(-a[p].y, a[p ^ XR].x, pr[j]) : fma(a[p].y, a[p ^ XR].y, pr[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) w[j & 3] = fma(pr[j], (j & 1) ? t[j >> 1].y : t[j >> 1].x, w[j & 3]);
     }
     return (w[0] + w[1]) + (w[2] + w[3]);
 }
@@ -96,18 +106,28 @@ __device__ __forceinline__ double dot_diag(const double2 (&a)[32], const double2
     return (w[0] + w[1]) + (w[2] + w[3]);
 }
 
+// sel = xr | im << 5 for DOT records; 0 / 32 = lower / upper half of a diagonal record.  All 64 values are cases, so
+// the switch compiles to ONE jump table.
 __device__ __forceinline__ double dot_dispatch(uint32_t sel, const double2 (&a)[32], const double2* __restrict__ tab) {
-#define QC_CASE(X)                            \
+#define QC_CASE(X)                              \
     case X: return dot_pairs<X, false>(a, tab); \
     case 32 + X: return dot_pairs<X, true>(a, tab);
-    switch (sel) {
+    switch (sel & 63u) {
+        case 0: return dot_diag<0>(a, tab);
+        case 32: return dot_diag<1>(a, tab);
         QC_CASE(1) QC_CASE(2) QC_CASE(3) QC_CASE(4) QC_CASE(5) QC_CASE(6) QC_CASE(7) QC_CASE(8) QC_CASE(9) QC_CASE(10)
         QC_CASE(11) QC_CASE(12) QC_CASE(13) QC_CASE(14) QC_CASE(15) QC_CASE(16) QC_CASE(17) QC_CASE(18) QC_CASE(19)
         QC_CASE(20) QC_CASE(21) QC_CASE(22) QC_CASE(23) QC_CASE(24) QC_CASE(25) QC_CASE(26) QC_CASE(27) QC_CASE(28)
         QC_CASE(29) QC_CASE(30) QC_CASE(31)
-        default: return 0.0;
     }
 #undef QC_CASE
+    return 0.0;
+}
+
+// (-1)^{popc(base & z_outer) + popc(org & z_rest)}: parity is linear over XOR, so one POPC does it
+__device__ __forceinline__ unsigned sign_parity(uint64_t base, uint32_t org, const uint4& hd) {
+    const uint32_t lo = (uint32_t)base & hd.x, hi = (uint32_t)(base >> 32) & hd.y;
+    return (unsigned)__popc(lo ^ hi ^ (org & hd.z));
 }
 
 // One CTA = 128 threads, 64 KB tile + the pass's blob (sub-cube headers + records, <= 44 KB) in shared memory;
@@ -129,9 +149,6 @@ __global__ void __launch_bounds__(kTileThreads, 2)
     uint64_t off_lo = 0;
 #pragma unroll
     for (int j = 0; j < 7; ++j) off_lo |= (uint64_t)((threadIdx.x >> j) & 1u) << pass.spos[j];
-    uint64_t off_hi[5];
-#pragma unroll
-    for (int j = 0; j < 5; ++j) off_hi[j] = 1ull << pass.spos[7 + j];
     double acc0 = 0.0, acc1 = 0.0;
 
     for (uint64_t tau = blockIdx.x; tau < n_tiles; tau += gridDim.x) {
@@ -152,7 +169,7 @@ __global__ void __launch_bounds__(kTileThreads, 2)
             uint64_t o = 0;
 #pragma unroll
             for (int j = 0; j < 5; ++j)
-                if (k & (1 << j)) o |= off_hi[j];
+                if (k & (1 << j)) o |= 1ull << pass.spos[7 + j];
             cp_async16(&tile[k2_swizzle((uint32_t)k * kTileThreads + threadIdx.x)], src + o);
         }
         cp_async_wait_all();
@@ -183,6 +200,21 @@ __global__ void __launch_bounds__(kTileThreads, 2)
                 a[p] = tile[off];
             }
             const uint4* rp = blob + b1.y;
+            // ---- simple quads of this cube (x = cube minus bit j): straight-line code, no per-record dispatch
+            const uint32_t quad_mask = (b1.x >> 8) & 31u;
+#define QC_QUAD(J)                                                                                   \
+    if (quad_mask & (1u << J)) {                                                                     \
+        const uint4 hd = *rp;                                                                        \
+        const double w = dot_pairs<31 ^ (1 << J), false>(a, reinterpret_cast<const double2*>(rp + 1)); \
+        if (J & 1)                                                                                   \
+            acc1 += apply_sign(w, sign_parity(base, org, hd));                                       \
+        else                                                                                         \
+            acc0 += apply_sign(w, sign_parity(base, org, hd));                                       \
+        rp += kDotUnits;                                                                             \
+    }
+            QC_QUAD(0) QC_QUAD(1) QC_QUAD(2) QC_QUAD(3) QC_QUAD(4)
+#undef QC_QUAD
+            // ---- generic records
             double A0 = 0.0, A1 = 0.0, A2 = 0.0, A3 = 0.0;
             for (uint32_t r = 0; r < b1.z; ++r) {
                 const uint4 hd = *rp;
@@ -196,13 +228,11 @@ __global__ void __launch_bounds__(kTileThreads, 2)
                         const uint4 eh = ep[0];
                         const double2 c01 = *reinterpret_cast<const double2*>(ep + 1);
                         const double2 c23 = *reinterpret_cast<const double2*>(ep + 2);
-                        const uint64_t zo = (uint64_t)eh.x | ((uint64_t)eh.y << 32);
-                        const unsigned par = (unsigned)__popcll(base & zo) + (unsigned)__popc(org & eh.z);
                         const double v = fma(c01.x, A0, c01.y * A1) + fma(c23.x, A2, c23.y * A3);
                         if (e & 1u)
-                            acc1 += apply_sign(v, par);
+                            acc1 += apply_sign(v, sign_parity(base, org, eh));
                         else
-                            acc0 += apply_sign(v, par);
+                            acc0 += apply_sign(v, sign_parity(base, org, eh));
                     }
                     rp = ep;
                     continue;
@@ -211,20 +241,12 @@ __global__ void __launch_bounds__(kTileThreads, 2)
                 // compiler hoists the products of EVERY switch case out of the loop (LICM) and spills.
 #pragma unroll
                 for (int p = 0; p < 32; ++p) asm volatile("" : "+d"(a[p].x), "+d"(a[p].y));
-                const double2* tab = reinterpret_cast<const double2*>(rp + 1);
-                double w;
-                if (kind == kRecDot)
-                    w = dot_dispatch(meta & 63u, a, tab);
-                else if (kind == kRecDiagLo)
-                    w = dot_diag<0>(a, tab);
-                else
-                    w = dot_diag<1>(a, tab);
+                const uint32_t sel = kind == kRecDot ? (meta & 63u) : (kind == kRecDiagHi ? 32u : 0u);
+                const double w = dot_dispatch(sel, a, reinterpret_cast<const double2*>(rp + 1));
                 rp += kDotUnits;
                 const uint32_t mode = meta_mode(meta);
                 if (mode == kModeAcc) {
-                    const uint64_t zo = (uint64_t)hd.x | ((uint64_t)hd.y << 32);
-                    const unsigned par = (unsigned)__popcll(base & zo) + (unsigned)__popc(org & hd.z);
-                    acc0 += apply_sign(w, par);
+                    acc0 += apply_sign(w, sign_parity(base, org, hd));
                 } else {
                     const uint32_t sl = meta_slot(meta);
                     const double prev = mode == kModeAdd ? (sl == 0 ? A0 : sl == 1 ? A1 : sl == 2 ? A2 : A3) : 0.0;

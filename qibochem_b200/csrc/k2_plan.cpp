@@ -87,6 +87,7 @@ struct Atom {
     std::vector<Unit16> units;
     uint32_t n_recs = 0;
     bool needs_setup = false;
+    int quad_slot = -1;  // j when this is the single record of a "simple quad" (xr = 31 ^ (1 << j))
 };
 struct GroupRecs {
     std::vector<Unit16> setup;
@@ -213,6 +214,9 @@ GroupRecs emit_group(const XG& g, const uint64_t* zs, const double* cs, uint64_t
         }
         out.atoms.push_back(std::move(atom));
     }
+    if (popc32(xr) == 4 && out.atoms.size() == 1 && out.atoms[0].n_recs == 1 && !out.atoms[0].needs_setup &&
+        tab_keys.size() == 1 && tab_keys[0].second == 0)
+        out.atoms[0].quad_slot = __builtin_ctz(31u ^ xr);
     return out;
 }
 
@@ -395,7 +399,8 @@ HostPlan* build_host_plan(int n, size_t T, const uint64_t* xs, const uint64_t* z
         // ---- emit the pass (split into several passes over the same S when its blob would exceed the cap)
         struct RB {
             TRBlock hdr;
-            std::vector<Unit16> recs;
+            std::vector<Unit16> quads[kRBits];  // simple-quad records by slot
+            std::vector<Unit16> recs;           // generic records
         };
         std::vector<RB> cur;       // sub-cube visits of the pass being assembled
         uint32_t cur_units = 0;    // headers + records
@@ -413,9 +418,14 @@ HostPlan* build_host_plan(int n, size_t T, const uint64_t* xs, const uint64_t* z
             for (RB& rb : cur) {
                 rb.hdr.rec_off = rec_off;
                 rec_off += (uint32_t)rb.recs.size();
+                for (int j = 0; j < kRBits; ++j) rec_off += (uint32_t)rb.quads[j].size();
                 push_units(plan->units, &rb.hdr, sizeof(TRBlock));
             }
-            for (RB& rb : cur) plan->units.insert(plan->units.end(), rb.recs.begin(), rb.recs.end());
+            for (RB& rb : cur) {
+                for (int j = 0; j < kRBits; ++j)
+                    plan->units.insert(plan->units.end(), rb.quads[j].begin(), rb.quads[j].end());
+                plan->units.insert(plan->units.end(), rb.recs.begin(), rb.recs.end());
+            }
             pass.blob_units = rec_off;
             plan->passes.push_back(pass);
             st.n_rblocks += cur.size();
@@ -464,7 +474,8 @@ HostPlan* build_host_plan(int n, size_t T, const uint64_t* xs, const uint64_t* z
             bool open = false;  // a visit of this sub-cube is open in `cur`
             uint32_t visit_groups = 0;
             auto open_visit = [&]() {
-                cur.push_back({blk, {}});
+                cur.push_back(RB());
+                cur.back().hdr = blk;
                 cur_units += kRBlockUnits;
                 open = true;
                 visit_groups = 0;
@@ -494,8 +505,13 @@ HostPlan* build_host_plan(int n, size_t T, const uint64_t* xs, const uint64_t* z
                         st.n_dot += gr.setup_recs;
                         setup_here = true;
                     }
-                    rb.recs.insert(rb.recs.end(), atom.units.begin(), atom.units.end());
-                    rb.hdr.n_recs += atom.n_recs;
+                    if (atom.quad_slot >= 0 && !((rb.hdr.quad_mask >> atom.quad_slot) & 1u)) {
+                        rb.quads[atom.quad_slot] = atom.units;
+                        rb.hdr.quad_mask |= (uint8_t)(1u << atom.quad_slot);
+                    } else {
+                        rb.recs.insert(rb.recs.end(), atom.units.begin(), atom.units.end());
+                        rb.hdr.n_recs += atom.n_recs;
+                    }
                     cur_units += (uint32_t)atom.units.size();
                     if (!atom.needs_setup) st.n_dot += atom.n_recs;
                     if (!counted) {
@@ -545,7 +561,20 @@ double check_host_plan(const HostPlan* plan, size_t T, const uint64_t* xs, const
                     if (k2_swizzle(1u << b) == blk.sbit[j]) seen |= 1u << b;
             if (seen != (1u << kTileBits) - 1u) return -1.0;
             uint32_t u = pass.blob_off + blk.rec_off;
-            for (uint32_t r = 0; r < blk.n_recs; ++r) {
+            const uint32_t n_quads = (uint32_t)popc32(blk.quad_mask);
+            {   // the quad records must be plain DOT/ACC/Re records of the announced masks, in ascending slot order
+                uint32_t uq = u;
+                for (int j = 0; j < kRBits; ++j) {
+                    if (!((blk.quad_mask >> j) & 1u)) continue;
+                    TRecHdr h;
+                    memcpy(&h, &plan->units[uq], sizeof(h));
+                    if (meta_kind(h.meta) != kRecDot || meta_mode(h.meta) != kModeAcc || meta_im(h.meta) != 0 ||
+                        meta_xr(h.meta) != (31u ^ (1u << j)))
+                        return -1.0;
+                    uq += kDotUnits;
+                }
+            }
+            for (uint32_t r = 0; r < n_quads + blk.n_recs; ++r) {
                 TRecHdr h;
                 memcpy(&h, &plan->units[u], sizeof(h));
                 const uint32_t units = meta_kind(h.meta) == kRecLin ? 1 + kLinEntryUnits * meta_count(h.meta) : kDotUnits;

@@ -42,9 +42,12 @@ struct TPass {             // kernel parameter (constant bank)
 struct TRBlock {           // 32 bytes = 2 units
     uint16_t sbit[kRBits]; // swizzled tile slot of each sub-cube bit
     uint8_t perm[kTileBits - kRBits];  // thread-index bit j -> tile-local position outside the sub-cube
-    uint8_t pad[3];
-    uint32_t rec_off;      // first record, in units from the start of the blob
-    uint32_t n_recs;
+    uint8_t quad_mask;     // bit j: the visit starts with a plain DOT/ACC/Re record for xr = 31 ^ (1 << j) ("simple
+                           // quad": the 4-bit x-mask that leaves out cube bit j), in ascending j -- the kernel runs
+                           // these from straight-line code without the per-record dispatch
+    uint8_t pad[2];
+    uint32_t rec_off;      // first record (quad records first), in units from the start of the blob
+    uint32_t n_recs;       // generic records following the popcount(quad_mask) quad records
     uint32_t n_groups;
 };
 static_assert(sizeof(TRBlock) == 32, "TRBlock layout");
