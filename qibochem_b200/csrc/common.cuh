@@ -83,7 +83,8 @@ struct qc_state {
     double* h_out = nullptr;       // pinned mirror of d_out
     double2* scratch_psi = nullptr;  // scratch copy of the shard (sampling), allocated lazily
     qc::Profiler prof;
-    qc::TiledPlan* k2plan = nullptr;  // cached plan of the tiled expectation (keyed by a hash of the term list)
+    std::vector<qc::TiledPlan*> k2plans;  // cached plans of the tiled expectation (keyed by a hash of the term list; LRU)
+    int k1_mode = 0;                  // 0 auto, 1 one HBM pass per fused run, 2 shared-memory tiles whenever a run fits
     int k2_mode = 0;                  // 0 auto, 1 force sweeps (one HBM pass per x-mask), 2 force tiles
     int ensure_partials(size_t doubles);
     int ensure_out(size_t doubles);

@@ -307,16 +307,27 @@ int run_tiled_expectation(qc_state* h, size_t T, const uint64_t* xs, const uint6
     hash = fnv1a(xs, T * 8, hash);
     hash = fnv1a(zs, T * 8, hash);
     hash = fnv1a(cs, T * 8, hash);
-    if (!h->k2plan || h->k2plan->hash != hash || h->k2plan->host->n != h->n) {
-        QC_CHECK(cudaStreamSynchronize(h->stream));
-        free_tiled_plan(h->k2plan);
-        h->k2plan = nullptr;
+    constexpr size_t kMaxCachedPlans = 8;  // a sharded energy walks through a few layouts, each with its own term list
+    TiledPlan* found = nullptr;
+    for (size_t i = 0; i < h->k2plans.size(); ++i)
+        if (h->k2plans[i]->hash == hash && h->k2plans[i]->host->n == h->n) {
+            found = h->k2plans[i];
+            h->k2plans.erase(h->k2plans.begin() + i);
+            break;
+        }
+    if (!found) {
         HostPlan* hp = build_host_plan(h->n, T, xs, zs, cs);
         QC_REQUIRE(hp != nullptr, "qc_expectation: could not build the tiled plan");
-        h->k2plan = upload_plan(hp, hash);
-        QC_REQUIRE(h->k2plan != nullptr, "qc_expectation: could not upload the tiled plan");
+        found = upload_plan(hp, hash);
+        QC_REQUIRE(found != nullptr, "qc_expectation: could not upload the tiled plan");
+        if (h->k2plans.size() >= kMaxCachedPlans) {
+            QC_CHECK(cudaStreamSynchronize(h->stream));  // the evicted plan may still be read by in-flight passes
+            free_tiled_plan(h->k2plans.front());
+            h->k2plans.erase(h->k2plans.begin());
+        }
     }
-    const TiledPlan* plan = h->k2plan;
+    h->k2plans.push_back(found);  // most recently used last
+    const TiledPlan* plan = found;
     const HostPlan* hp = plan->host;
     const size_t smem = (size_t)kTileSize * sizeof(double2) + (size_t)kBlobCapUnits * 16;
     const int ctas = 2;

@@ -170,7 +170,7 @@ int qc_destroy(qc_state* h) {
     if (h->h_out) cudaFreeHost(h->h_out);
     h->arena.release();
     h->prof.release();
-    qc::free_tiled_plan(h->k2plan);
+    for (qc::TiledPlan* p : h->k2plans) qc::free_tiled_plan(p);
     if (h->owns_stream) cudaStreamDestroy(h->stream);
     delete h;
     return 0;
@@ -226,6 +226,11 @@ int qc_set_option(qc_state* h, const char* key, int64_t value) {
     if (strcmp(key, "k2_mode") == 0) {
         QC_REQUIRE(value >= 0 && value <= 2, "qc_set_option: k2_mode must be 0 (auto), 1 (sweeps) or 2 (tiles)");
         h->k2_mode = (int)value;
+        return 0;
+    }
+    if (strcmp(key, "k1_mode") == 0) {
+        QC_REQUIRE(value >= 0 && value <= 2, "qc_set_option: k1_mode must be 0 (auto), 1 (one pass per run) or 2 (tiles)");
+        h->k1_mode = (int)value;
         return 0;
     }
     qc::set_error(std::string("qc_set_option: unknown key ") + key);

@@ -325,3 +325,64 @@ def test_tiled_expectation_on_ucc_state(DeviceState):
 
     ref = OC.expectation_masks(psi, n, hx, hz, hc)
     assert abs(e1 - ref) < E_TOL and abs(e2 - ref) < E_TOL and abs(e0 - ref) < E_TOL
+
+
+@pytest.mark.parametrize("n", [12, 13, 15, 16])
+def test_tiled_rotation_batches_match_oracle(DeviceState, n):
+    """K1T: consecutive runs whose x-masks fit a 12-bit tile are applied in one in-place pass.  Random fused runs with
+    z / support bits inside AND outside the tile, diagonal runs, low-x runs; tiles == one-pass-per-run == oracle."""
+    rng = np.random.default_rng(50 + n)
+    psi = random_state(n, 5 * n + 2)
+    xs, zs, phis = [], [], []
+    pool = rng.choice(n, size=7, replace=False)  # x-masks drawn from 7 bits: batches form
+    for run in range(14):
+        if run % 5 == 4:
+            x = 0
+        else:
+            w = int(rng.integers(1, 5))
+            x = int(sum(1 << int(b) for b in rng.choice(pool, size=w, replace=False)))
+        z0 = int(rng.integers(0, 2**n))
+        members = [z0]
+        for _ in range(30):
+            dz = int(rng.integers(0, 2**n)) & (x | (int(rng.integers(0, 2**n)) & (0x3 | 1 << (n - 1) | 1 << (n - 2))))
+            if bin(x & dz).count("1") % 2 == 0 and (z0 ^ dz) not in members:
+                members.append(z0 ^ dz)
+            if len(members) == 6:
+                break
+        for z in members:
+            xs.append(x), zs.append(z), phis.append(float(rng.uniform(-1, 1)))
+    # a string too wide for a tile in the middle of the stream
+    xs.insert(20, (1 << n) - 1), zs.insert(20, 5), phis.insert(20, 0.3)
+    ref = psi.copy()
+    for x, z, p in zip(xs, zs, phis):
+        ref = O.apply_pauli_rotation(ref, x, z, p)
+    with DeviceState(n) as st:
+        results = {}
+        for mode in (1, 0, 2):
+            st.set_option("k1_mode", mode)
+            st.from_numpy(psi)
+            passes = st.apply_pauli_rotations(xs, zs, phis)
+            results[mode] = (passes, st.to_numpy())
+            assert np.abs(results[mode][1] - ref).max() < AMP_TOL, f"k1_mode={mode}"
+        assert results[0][0] < results[1][0]  # batching saved passes
+
+
+def test_tiled_rotations_on_uccsd_stream(DeviceState):
+    """UCCSD prefix at 16 qubits (reference excitation order): batched passes == one pass per excitation == C oracle."""
+    from oracle import oracle_c as OC
+    from qibochem_b200 import synthetic
+
+    n, ne = 16, 6
+    rx, rz, ra, n_exc = synthetic.uccsd_rotation_stream(n, ne, max_excitations=60)
+    ref = np.zeros(2**n, dtype=np.complex128)
+    ref[synthetic.hf_index(n, ne)] = 1.0
+    for x, z, a in zip(rx.tolist(), rz.tolist(), ra.tolist()):
+        OC.pauli_rotation(ref, n, x, z, a)
+    with DeviceState(n) as st:
+        out = {}
+        for mode in (1, 0):
+            st.set_option("k1_mode", mode)
+            st.set_basis_state(synthetic.hf_index(n, ne))
+            out[mode] = (st.apply_pauli_rotations(rx, rz, ra), st.to_numpy())
+            assert np.abs(out[mode][1] - ref).max() < AMP_TOL
+        assert out[1][0] == n_exc and out[0][0] * 2 < n_exc
