@@ -170,10 +170,18 @@ __device__ __forceinline__ double2 mul_pow_minus_i(int m, double2 v) {
     }
 }
 
+constexpr int kTileRunTable = 32;  // (cos, sin) entries per run staged in shared memory (support <= 5 bits)
+
 __global__ void __launch_bounds__(kRotTileThreads, 3)
     rot_tiled_kernel(double2* __restrict__ psi, int n, const TileBatch batch, const double2* __restrict__ table) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double2* tile = reinterpret_cast<double2*>(smem_raw);
+    double2* stab = tile + kRotTileSize;  // [n_runs][kTileRunTable]
+    for (int e = threadIdx.x; e < batch.n_runs * kTileRunTable; e += kRotTileThreads) {
+        const TileRun& d = batch.run[e / kTileRunTable];
+        const int k = e % kTileRunTable;
+        if (k < (1 << (d.n_sup_l + __popcll(d.sup_outer)))) stab[e] = __ldg(&table[d.table_off + k]);
+    }
     const uint64_t n_tiles = 1ull << (n - kRotTileBits);
     // amplitude offset of tile slot t = k * 256 + tid: low 8 tile bits from tid, high 4 from k
     uint64_t off_lo = 0;
@@ -191,7 +199,7 @@ __global__ void __launch_bounds__(kRotTileThreads, 3)
             }
         }
         double2* src = psi + base + off_lo;
-        __syncthreads();  // the previous tile has been written back
+        __syncthreads();  // the previous tile has been written back (first time: tables staged)
 #pragma unroll
         for (int k = 0; k < kRotTileSize / kRotTileThreads; ++k) {
             uint64_t o = 0;
@@ -206,28 +214,36 @@ __global__ void __launch_bounds__(kRotTileThreads, 3)
 
         for (int r = 0; r < batch.n_runs; ++r) {
             const TileRun& d = batch.run[r];
-            const double2* tab = table + d.table_off;
+            const double2* tab = stab + r * kTileRunTable;
             uint32_t outer_idx = 0;
             if (d.sup_outer) outer_idx = gather_bits(base, d.sup_outer) << d.n_sup_l;
             const unsigned outer_par = (unsigned)__popcll(base & d.z0_outer);
+            // A thread's slots share the part that comes from tid; the part from k is warp-uniform.
             if (d.xl == 0) {
-#pragma unroll 4
+                const uint32_t t0 = threadIdx.x;
+                const uint32_t idx0 = outer_idx | (d.sup_l ? pext32(t0, d.sup_l) : 0u);
+                const unsigned par0 = outer_par + (unsigned)__popc(t0 & d.z0_l);
+#pragma unroll
                 for (int k = 0; k < kRotTileSize / kRotTileThreads; ++k) {
-                    const uint32_t t = (uint32_t)k * kRotTileThreads + threadIdx.x;
+                    const uint32_t tk = (uint32_t)k * kRotTileThreads;
+                    const uint32_t t = t0 | tk;
                     const double2 a = tile[t];
-                    const double2 cs = __ldg(&tab[outer_idx | (d.sup_l ? pext32(t, d.sup_l) : 0u)]);
-                    const unsigned par = outer_par + (unsigned)__popc(t & d.z0_l);
+                    const double2 cs = tab[idx0 | (d.sup_l ? pext32(tk, d.sup_l) : 0u)];
+                    const unsigned par = par0 + (unsigned)__popc(tk & d.z0_l);
                     const double ms = (par & 1u) ? cs.y : -cs.y;  // multiply by (c - i s0 s)
                     tile[t] = make_double2(cs.x * a.x - ms * a.y, cs.x * a.y + ms * a.x);
                 }
             } else {
-#pragma unroll 4
+                const uint32_t t0 = (uint32_t)insert_zero_bit(threadIdx.x, d.hb_l);
+                const uint32_t idx0 = outer_idx | (d.sup_l ? pext32(t0, d.sup_l) : 0u);
+                const unsigned par0 = outer_par + (unsigned)__popc(t0 & d.z0_l);
+#pragma unroll
                 for (int k = 0; k < kRotTileSize / 2 / kRotTileThreads; ++k) {
-                    const uint32_t q = (uint32_t)k * kRotTileThreads + threadIdx.x;
-                    const uint32_t t = (uint32_t)insert_zero_bit(q, d.hb_l), u = t ^ d.xl;
+                    const uint32_t tk = (uint32_t)insert_zero_bit((uint32_t)k * kRotTileThreads, d.hb_l);
+                    const uint32_t t = t0 | tk, u = t ^ d.xl;
                     const double2 a = tile[t], b = tile[u];
-                    const double2 cs = __ldg(&tab[outer_idx | (d.sup_l ? pext32(t, d.sup_l) : 0u)]);
-                    const unsigned par = outer_par + (unsigned)__popc(t & d.z0_l);
+                    const double2 cs = tab[idx0 | (d.sup_l ? pext32(tk, d.sup_l) : 0u)];
+                    const unsigned par = par0 + (unsigned)__popc(tk & d.z0_l);
                     const double f = (par & 1u) ? -cs.y : cs.y;
                     const double2 ub = mul_pow_minus_i(d.ma, b), ua = mul_pow_minus_i(d.mb, a);
                     tile[t] = make_double2(cs.x * a.x + f * ub.x, cs.x * a.y + f * ub.y);
@@ -318,8 +334,9 @@ extern "C" int qc_apply_pauli_rotations(qc_state* h, size_t R, const uint64_t* x
         while (i < runs.size()) {
             uint64_t U = runs[i].x;
             size_t j = i + 1;
-            if (tiles_ok && __builtin_popcountll(U | low) <= kRotTileBits) {
-                while (j < runs.size() && j - i < (size_t)kMaxBatchRuns &&
+            auto small = [&](const Run& g) { return (1 << __builtin_popcountll(g.sup)) <= kTileRunTable; };
+            if (tiles_ok && small(runs[i]) && __builtin_popcountll(U | low) <= kRotTileBits) {
+                while (j < runs.size() && j - i < (size_t)kMaxBatchRuns && small(runs[j]) &&
                        __builtin_popcountll(U | runs[j].x | low) <= kRotTileBits) {
                     U |= runs[j].x;
                     ++j;
@@ -385,7 +402,7 @@ extern "C" int qc_apply_pauli_rotations(qc_state* h, size_t R, const uint64_t* x
                              h->stream));
     const double2* dtab = (const double2*)h->arena.dev;
 
-    const size_t tile_smem = (size_t)kRotTileSize * sizeof(double2);
+    const size_t tile_smem = (size_t)(kRotTileSize + kMaxBatchRuns * kTileRunTable) * sizeof(double2);
     for (const Batch& bt : batches) {
         LaunchScope ls(h, kK1Rotation, 32.0 * (double)h->dim);  // every amplitude read + written once per pass
         if (bt.S) {
