@@ -289,15 +289,19 @@ def main():
     b_n = 16.0 * 2.0 ** wl["n"]
     # HBM bytes a launch really moves: a tiled K2 pass reads the shard once however many x-masks it serves
     hbm_actual = {"k2_tiled": b_n, "k2_expectation": None, "k1_rotation": 2 * b_n}.get(dom)
+    fp64 = k2_fp64_roofline(wl, prof, args) if dom == "k2_tiled" else None
     roofline = {
         "kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
         "note": ("achieved = algorithmic bytes (SURVEY 8d: 16*2^n per distinct x-mask) / device time; the tiled kernel "
                  "serves many x-masks from one HBM read, so this exceeds the HBM peak by design -- hbm_actual_GBps is "
-                 "what crosses the memory bus; the kernel is bound by shared-memory bandwidth and FP64 issue")
+                 "what crosses the memory bus; the kernel is bound by FP64 issue and shared-memory bandwidth (see fp64)")
         if dom == "k2_tiled" else "achieved = algorithmic bytes / device time",
         "hbm_actual_GBps": (hbm_actual * d["launches"] / 1e9 / (d["ms"] / 1e3)) if (hbm_actual and d["ms"]) else None,
         "peak_source": "MEASURED_PEAKS.json hbm_gbs (copy, read+write)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
-        "traffic": None,
+        # dram__bytes_read.sum + dram__bytes_write.sum per K2T launch from the committed ncu --set full capture of this
+        # command at 30 qubits (profiles/r1_ncu_full_k2t_30q_v5.csv: 17.18 GB read + ~5 MB written per pass)
+        "traffic": 17.187e9 if (dom == "k2_tiled" and wl["n"] == 30) else None,
+        "fp64": fp64,
         "launches": d["launches"], "avg_launch_ms": d["ms"] / max(d["launches"], 1),
         "algorithmic_bytes_per_launch": d["bytes"] / max(d["launches"], 1),
         "share_of_step": d["ms"] / dev_ms,
@@ -318,6 +322,33 @@ def main():
         "clocks": clock_info, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
     }  # fmt: skip
     print(json.dumps(line))
+
+
+def k2_fp64_roofline(wl, prof, args):
+    """What really bounds the tiled expectation: FP64 issue.  FP64 instructions per pass are counted from the plan
+    (DOT record: 48 DMUL/DFMA + 4 DADD per thread, LIN entry: 4 + 2) and compared with the DFMA rate measured on this
+    pool's B200 by tools/ubench/fp64_pipe.cu (profiles/r1_fp64_pipe_b200.txt: 63.4 DFMA/clk/SM = 34.9 TFLOP/s)."""
+    import ctypes as C
+
+    from qibochem_b200 import _native
+
+    lib = _native.load()
+    stats = np.zeros(16, dtype=np.uint64)
+    u64p, f64p = C.POINTER(C.c_uint64), C.POINTER(C.c_double)
+    hx, hz, hc = (np.ascontiguousarray(wl[k]) for k in ("hx", "hz", "hc"))
+    rc = lib.qc_k2_plan_stats(wl["n"], hx.size, hx.ctypes.data_as(u64p), hz.ctypes.data_as(u64p), hc.ctypes.data_as(f64p),
+                              stats.ctypes.data_as(u64p), None)  # fmt: skip
+    if rc != 0 or not prof["k2_tiled"]["ms"]:
+        return None
+    n_pass, n_cubes, n_dot, n_lin = (int(stats[k]) for k in (2, 3, 4, 5))
+    threads = 2.0 ** wl["n"] / 32.0  # one thread per 32-amplitude sub-cube
+    fp64_instr = (52.0 * n_dot + 6.0 * n_lin) * threads  # per energy evaluation
+    seconds = prof["k2_tiled"]["ms"] / 1e3 / args.steps
+    peak_instr = 63.4 * 148 * 1.965e9
+    return {"unit": "FP64 instr/s (DFMA-rate)", "achieved": fp64_instr / seconds, "peak": peak_instr, "frac": fp64_instr / seconds / peak_instr,
+            "peak_source": "tools/ubench/fp64_pipe.cu on this pool's B200: 63.4 DFMA/clk/SM x 148 SMs x 1.965 GHz (34.9 TFLOP/s)",
+            "plan": {"hbm_passes": n_pass, "sub_cube_gathers": n_cubes, "dot_records": n_dot, "lin_entries": n_lin},
+            "shared_memory_gather_bytes_per_eval": n_cubes * 16.0 * 2.0 ** wl["n"]}  # fmt: skip
 
 
 def measure_e2e(wl, args, st):
