@@ -386,3 +386,55 @@ def test_tiled_rotations_on_uccsd_stream(DeviceState):
             out[mode] = (st.apply_pauli_rotations(rx, rz, ra), st.to_numpy())
             assert np.abs(out[mode][1] - ref).max() < AMP_TOL
         assert out[1][0] == n_exc and out[0][0] * 2 < n_exc
+
+
+def test_full_size_30q_properties(DeviceState):
+    """BASELINE configs[3] size (30 qubits, 17 GB state): size-independent properties instead of an oracle run.
+    (a) unitarity: norm stays 1; (b) known answer: a Z-only Hamiltonian on a basis state; (c) tile-batched rotations ==
+    one pass per excitation; (d) tiled expectation == per-x-mask sweeps on a term subset; (e) linearity in the
+    coefficients; (f) U^-1 U = 1: the reversed stream with negated angles returns the HF determinant."""
+    import torch
+
+    if torch.cuda.get_device_properties(0).total_memory < 40e9:
+        pytest.skip("needs > 40 GB of HBM")
+    from qibochem_b200 import synthetic
+
+    n, ne = 30, 14
+    rx, rz, ra, _ = synthetic.uccsd_rotation_stream(n, ne, max_excitations=24)
+    hx, hz, hc, _ = synthetic.molecular_like_hamiltonian(n, 100_000)
+    hf = synthetic.hf_index(n, ne)
+    rng = np.random.default_rng(30)
+    sub = np.sort(rng.choice(hx.size, size=48, replace=False))
+    big = np.sort(rng.choice(hx.size, size=12_000, replace=False))
+    with DeviceState(n) as st:
+        # (b) diagonal known answer on |HF>
+        st.set_basis_state(hf)
+        diag = hx == 0
+        known = float(np.sum(hc[diag] * np.where(np.array([bin(hf & int(z)).count("1") & 1 for z in hz[diag]]) == 1, -1.0, 1.0)))
+        assert abs(st.expectation(hx[diag], hz[diag], hc[diag]) - known) < E_TOL
+        # (c) batched vs per-run rotations, (a) norm
+        energies = {}
+        for mode in (1, 0):
+            st.set_option("k1_mode", mode)
+            st.set_basis_state(hf)
+            passes = st.apply_pauli_rotations(rx, rz, ra)
+            assert abs(st.norm2() - 1.0) < 1e-12
+            st.set_option("k2_mode", 1)
+            energies[mode] = (passes, st.expectation(hx[sub], hz[sub], hc[sub]))
+        assert energies[0][0] < energies[1][0]
+        assert abs(energies[0][1] - energies[1][1]) < E_TOL
+        # (d) tiles vs sweeps on the same subset (state: the batched one)
+        st.set_option("k2_mode", 2)
+        assert abs(st.expectation(hx[sub], hz[sub], hc[sub]) - energies[0][1]) < E_TOL
+        # (e) linearity on a 12k-term subset through the tiled path
+        st.set_option("k2_mode", 0)
+        c1 = hc[big]
+        c2 = rng.normal(scale=0.05, size=big.size)
+        e1 = st.expectation(hx[big], hz[big], c1)
+        e2 = st.expectation(hx[big], hz[big], c2)
+        e12 = st.expectation(hx[big], hz[big], c1 + 2.0 * c2)
+        assert abs(e12 - (e1 + 2.0 * e2)) < 1e-9
+        # (f) inverse stream
+        st.apply_pauli_rotations(rx[::-1], rz[::-1], -ra[::-1])
+        amp = st.to_numpy(offset=hf, count=1)[0]
+        assert abs(amp - 1.0) < 1e-12 and abs(st.norm2() - 1.0) < 1e-12
