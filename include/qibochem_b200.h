@@ -80,6 +80,15 @@ int qc_set_option(qc_state* h, const char* key, int64_t value);
  * W_x(i) = sum_k d_k (-1)^{popcount(i & z_k)}; negative if some x-mask is not served exactly once. */
 int qc_k2_plan_stats(int n_local_qubits, size_t T, const uint64_t* xmask, const uint64_t* zmask, const double* coeff,
                      uint64_t* stats_out, double* check_out);
+/* ---- adjoint-mode gradient (replaces qibo.derivative.parameter_shift, used at doc/source/tutorials/adaptive.rst:46-61,
+ *      :118-141 of the reference: two full energy evaluations PER parameter) ------------------------------------- */
+/* Precondition: the handle holds psi = U psi0 where U is the given rotation program (qc_apply_pauli_rotations with
+ * the same arrays).  energy_out <- sum_k coeff[k] Re<psi|P_k|psi>;  grad_out[r] <- dE/d angle[r] for all R rotations,
+ * from lambda = H psi and one backward walk over the fused runs (dE/dphi_r = Im<lambda_r|P_r|psi_r>).  Postcondition:
+ * the handle holds psi0 again (the program has been un-applied).  Uses one scratch array of the shard's size. */
+int qc_energy_gradient(qc_state* h, size_t R, const uint64_t* xmask, const uint64_t* zmask, const double* angle,
+                       size_t T, const uint64_t* hxmask, const uint64_t* hzmask, const double* coeff,
+                       double* energy_out, double* grad_out);
 /* <psi|psi> over this shard. */
 int qc_norm2(qc_state* h, double* out);
 
@@ -106,7 +115,7 @@ int qc_frequencies(qc_state* h, const uint64_t* samples, size_t n, int on_device
 
 /* ---- live profiler / launch counter (bench.py: roofline of the dominant kernel, gpu_launches) ----------------- */
 /* Kernel classes: 0 K0 init, 1 K1 rotation pass, 2 K2 expectation sweeps, 3 reductions, 4 K5 sampling, 5 K3 shot
- * statistics, 6 K4 exchange, 7 K2 tiled expectation passes.  Launch counts and algorithmic bytes are always accumulated; when enabled, every
+ * statistics, 6 K4 exchange, 7 K2 tiled expectation passes, 8 gradient sweeps.  Launch counts and algorithmic bytes are always accumulated; when enabled, every
  * launch is additionally bracketed by CUDA events on the handle's stream and its device time accumulated. */
 int qc_profile_enable(qc_state* h, int enabled);
 int qc_profile_reset(qc_state* h);

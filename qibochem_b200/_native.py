@@ -32,6 +32,7 @@ SIGNATURES = {
     "qc_expectation": (C.c_int, [_vp, C.c_size_t, _u64p, _u64p, _f64p, _f64p, _f64p, C.POINTER(C.c_int)]),
     "qc_set_option": (C.c_int, [_vp, C.c_char_p, C.c_int64]),
     "qc_k2_plan_stats": (C.c_int, [C.c_int, C.c_size_t, _u64p, _u64p, _f64p, _u64p, _f64p]),
+    "qc_energy_gradient": (C.c_int, [_vp, C.c_size_t, _u64p, _u64p, _f64p, C.c_size_t, _u64p, _u64p, _f64p, _f64p, _f64p]),
     "qc_norm2": (C.c_int, [_vp, _f64p]),
     "qc_sample": (C.c_int, [_vp, C.c_uint64, C.c_uint64, C.c_size_t, C.c_uint64, C.c_uint64, _vp, C.c_int, _f64p]),
     "qc_parity_sums": (C.c_int, [_vp, _vp, _vp, C.c_size_t, C.c_int, _u64p, C.c_size_t, _i64p]),

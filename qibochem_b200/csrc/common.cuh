@@ -41,7 +41,7 @@ struct Arena {
 };
 
 // Kernel classes for the launch counter / live profiler (qc_profile_*)
-enum KernelClass { kK0Init = 0, kK1Rotation = 1, kK2Expectation = 2, kReduce = 3, kK5Sampling = 4, kK3Shots = 5, kK4Exchange = 6, kK2Tiled = 7, kNumClasses = 8 };
+enum KernelClass { kK0Init = 0, kK1Rotation = 1, kK2Expectation = 2, kReduce = 3, kK5Sampling = 4, kK3Shots = 5, kK4Exchange = 6, kK2Tiled = 7, kGradient = 8, kNumClasses = 9 };
 
 struct TiledPlan;  // expectation_tiled.cu
 void free_tiled_plan(TiledPlan* p);

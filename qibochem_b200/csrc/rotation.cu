@@ -305,19 +305,19 @@ static void plan_runs(size_t R, const uint64_t* xs, const uint64_t* zs, std::vec
     }
 }
 
-}  // namespace qc
 
-extern "C" int qc_apply_pauli_rotations(qc_state* h, size_t R, const uint64_t* xmask, const uint64_t* zmask,
-                                        const double* angle, int* n_passes_out) {
-    using namespace qc;
-    QC_REQUIRE(h, "qc_apply_pauli_rotations: null handle");
-    if (n_passes_out) *n_passes_out = 0;
-    if (R == 0) return 0;
-    QC_REQUIRE(xmask && zmask && angle, "qc_apply_pauli_rotations: null array");
-    for (size_t r = 0; r < R; ++r)
-        QC_REQUIRE(xmask[r] < h->dim && zmask[r] < h->dim, "qc_apply_pauli_rotations: mask has bits outside the shard");
-    QC_CHECK(cudaSetDevice(h->device));
 
+// Fused runs of a string list (first string, count) for callers that walk a program run by run (gradient.cu).
+void plan_rotation_runs(size_t R, const uint64_t* xs, const uint64_t* zs, std::vector<std::pair<size_t, size_t>>& out) {
+    std::vector<Run> runs;
+    plan_runs(R, xs, zs, runs);
+    out.clear();
+    for (const Run& g : runs) out.push_back({g.first, g.count});
+}
+
+// Applies the rotations to `target` (a shard-sized array of this handle: psi itself or the scratch array).
+int apply_rotations_to(qc_state* h, double2* target, size_t R, const uint64_t* xmask, const uint64_t* zmask,
+                       const double* angle, int k1_mode, int* n_passes_out) {
     std::vector<Run> runs;
     plan_runs(R, xmask, zmask, runs);
 
@@ -328,7 +328,7 @@ extern "C" int qc_apply_pauli_rotations(qc_state* h, size_t R, const uint64_t* x
     };
     std::vector<Batch> batches;
     {
-        const bool tiles_ok = h->n >= kRotTileBits && h->k1_mode != 1;
+        const bool tiles_ok = h->n >= kRotTileBits && k1_mode != 1;
         const uint64_t low = 7ull;
         size_t i = 0;
         while (i < runs.size()) {
@@ -341,7 +341,7 @@ extern "C" int qc_apply_pauli_rotations(qc_state* h, size_t R, const uint64_t* x
                     U |= runs[j].x;
                     ++j;
                 }
-                if (j - i >= 2 || h->k1_mode == 2) {
+                if (j - i >= 2 || k1_mode == 2) {
                     uint64_t S = U | low;
                     for (int b = 0; __builtin_popcountll(S) < kRotTileBits; ++b) S |= 1ull << b;
                     batches.push_back({i, j - i, S});
@@ -443,7 +443,7 @@ extern "C" int qc_apply_pauli_rotations(qc_state* h, size_t R, const uint64_t* x
             QC_CHECK(cudaFuncSetAttribute(rot_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem));
             const uint64_t n_tiles = 1ull << (h->n - kRotTileBits);
             const int nb = (int)std::min<uint64_t>(n_tiles, (uint64_t)h->sm_count * 3);
-            rot_tiled_kernel<<<nb, kRotTileThreads, tile_smem, h->stream>>>(h->psi, h->n, tb, dtab);
+            rot_tiled_kernel<<<nb, kRotTileThreads, tile_smem, h->stream>>>(target, h->n, tb, dtab);
             continue;
         }
         const Run& g = runs[bt.first];
@@ -458,17 +458,32 @@ extern "C" int qc_apply_pauli_rotations(qc_state* h, size_t R, const uint64_t* x
         d.table_off = table_off[bt.first];
         if (d.x == 0) {
             const int nb = grid_for(h->dim, 4, h->sm_count);
-            rot_diag_kernel<4><<<nb, kThreads, 0, h->stream>>>(h->psi, h->dim, d, dtab);
+            rot_diag_kernel<4><<<nb, kThreads, 0, h->stream>>>(target, h->dim, d, dtab);
         } else if (d.hb < 5) {
             const int nb = grid_for(h->dim, 4, h->sm_count);
-            rot_lowx_kernel<<<nb, kThreads, 0, h->stream>>>(h->psi, h->dim, d, dtab);
+            rot_lowx_kernel<<<nb, kThreads, 0, h->stream>>>(target, h->dim, d, dtab);
         } else {
             const uint64_t npairs = h->dim >> 1;
             const int nb = grid_for(npairs, 4, h->sm_count);
-            rot_pairs_kernel<4><<<nb, kThreads, 0, h->stream>>>(h->psi, npairs, d, dtab);
+            rot_pairs_kernel<4><<<nb, kThreads, 0, h->stream>>>(target, npairs, d, dtab);
         }
     }
     QC_CHECK(cudaGetLastError());
     if (n_passes_out) *n_passes_out = (int)batches.size();
     return 0;
+}
+
+}  // namespace qc
+
+extern "C" int qc_apply_pauli_rotations(qc_state* h, size_t R, const uint64_t* xmask, const uint64_t* zmask,
+                                        const double* angle, int* n_passes_out) {
+    using namespace qc;
+    QC_REQUIRE(h, "qc_apply_pauli_rotations: null handle");
+    if (n_passes_out) *n_passes_out = 0;
+    if (R == 0) return 0;
+    QC_REQUIRE(xmask && zmask && angle, "qc_apply_pauli_rotations: null array");
+    for (size_t r = 0; r < R; ++r)
+        QC_REQUIRE(xmask[r] < h->dim && zmask[r] < h->dim, "qc_apply_pauli_rotations: mask has bits outside the shard");
+    QC_CHECK(cudaSetDevice(h->device));
+    return apply_rotations_to(h, h->psi, R, xmask, zmask, angle, h->k1_mode, n_passes_out);
 }

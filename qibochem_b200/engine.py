@@ -116,6 +116,24 @@ class DeviceState:
         self.last_sweeps = sweeps.value
         return (e.value, pt) if per_term else e.value
 
+    def energy_gradient(self, rxmask, rzmask, angle, hxmask, hzmask, coeff):
+        """Adjoint-mode gradient: the state must hold U|psi0> for the given rotation program.  Returns
+        ``(sum_k c_k Re<psi|P_k|psi>, dE/d angle[R])`` and leaves |psi0> in the state."""
+        rx, rz, ra = _u64(rxmask), _u64(rzmask), _f64(angle)
+        hx, hz, hc = _u64(hxmask), _u64(hzmask), _f64(coeff)
+        if not (rx.shape == rz.shape == ra.shape and hx.shape == hz.shape == hc.shape and rx.ndim == hx.ndim == 1):
+            raise ValueError("mask / angle / coefficient arrays must be 1-d and of matching lengths")
+        e = C.c_double(0.0)
+        grad = np.zeros(rx.size, dtype=np.float64)
+        _native.check(
+            self._lib.qc_energy_gradient(
+                self._h, rx.size, _ptr(rx, C.c_uint64), _ptr(rz, C.c_uint64), _ptr(ra, C.c_double),
+                hx.size, _ptr(hx, C.c_uint64), _ptr(hz, C.c_uint64), _ptr(hc, C.c_double), C.byref(e), _ptr(grad, C.c_double),
+            ),
+            "qc_energy_gradient",
+        )  # fmt: skip
+        return e.value, grad
+
     def norm2(self) -> float:
         v = C.c_double(0.0)
         _native.check(self._lib.qc_norm2(self._h, C.byref(v)), "qc_norm2")
@@ -211,7 +229,7 @@ class DeviceState:
         )  # fmt: skip
 
     # -- profiler ----------------------------------------------------------------------------------------------
-    KERNEL_CLASSES = ("k0_init", "k1_rotation", "k2_expectation", "reduce", "k5_sampling", "k3_shots", "k4_exchange", "k2_tiled")
+    KERNEL_CLASSES = ("k0_init", "k1_rotation", "k2_expectation", "reduce", "k5_sampling", "k3_shots", "k4_exchange", "k2_tiled", "gradient")
 
     def set_option(self, key: str, value: int) -> None:
         """e.g. ``set_option("k2_mode", 1)``: 0 auto, 1 sweeps (one HBM pass per x-mask), 2 tiles."""

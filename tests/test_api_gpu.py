@@ -302,3 +302,24 @@ def test_result_frequencies_protocol():
     c.add([g.H(0), g.S(0)])  # |+i>
     c.add(g.M(0, basis=g.Y))
     assert dict(c(nshots=50).frequencies()) == {"0": 50}
+
+
+def test_adjoint_gradient_equals_parameter_shift_on_uccsd():
+    """qibochem_b200.derivative: all partial derivatives from one adjoint pass == qibo-style parameter_shift per
+    parameter (doc/source/tutorials/adaptive.rst:46-61 of the reference), on a molecule-shaped UCCSD circuit."""
+    A = _api()
+    from qibochem_b200.derivative import adjoint_gradient, parameter_shift
+
+    mol = F.synthetic_molecule(4, 4, 1)
+    ham = mol.hamiltonian()
+    circuit = A["hf_circuit"](mol.nso, 4) + A["ucc_circuit"](mol.nso, [0, 1, 4, 5], 0.21) + A["ucc_circuit"](mol.nso, [1, 7], -0.4)
+    circuit.add(A["gates"].RY(2, 0.3))
+    circuit.add(A["gates"].CNOT(2, 5))
+    circuit.add(A["gates"].RX(5, -0.7))
+    e, grad = adjoint_gradient(circuit, ham)
+    assert e == pytest.approx(ham.expectation(circuit), abs=1e-10)
+    assert grad.shape == (len(circuit.get_parameters()),)
+    for k in range(0, grad.size, 3):
+        assert grad[k] == pytest.approx(parameter_shift(circuit, ham, k), abs=1e-9)
+    with pytest.raises(ValueError):
+        parameter_shift(circuit, ham, grad.size)
