@@ -13,7 +13,7 @@ def main_sharded(args, n: int, nelec: int) -> None:
     import torch
     import torch.distributed as dist
 
-    from bench import METRIC, ClockSampler, config_dict, workload
+    from bench import METRIC, ClockSampler, config_dict, unit_for, workload
     from qibochem_b200.engine import DeviceState
     from qibochem_b200.sharded import IpcExchanger, ShardedState
 
@@ -75,13 +75,13 @@ def main_sharded(args, n: int, nelec: int) -> None:
         achieved = d["bytes"] / 1e9 / (d["ms"] / 1e3) if d["ms"] else 0.0
         nvlink = (ex.swap_bytes / 1e9 / ex.swap_seconds) if ex.swap_seconds else None
         line = {
-            "metric": METRIC, "value": scale * 1e3 / ms_per_step, "unit": "evals/s (30-qubit equivalent: x 2^(n-30))",
+            "metric": METRIC, "value": scale * 1e3 / ms_per_step, "unit": unit_for(n),
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 (complex128)",
             "data": "synthetic", "config": config_dict(wl, args),
             "raw_evals_per_sec": 1e3 / ms_per_step, "energy": energies[-1], "energy_spread": float(np.ptp(energies)),
             "clocks": clock_info,
-            "e2e": {"value": scale * 1e3 * args.steps / wall_ms, "unit": "evals/s (30-qubit equivalent)",
+            "e2e": {"value": scale * 1e3 * args.steps / wall_ms, "unit": unit_for(n),
                     "h2d_bytes_per_step": int(wl["rx"].size * 24 + wl["hx"].size * 24) * world, "d2h_bytes_per_step": 8 * world,
                     "api": "ShardedState.apply_pauli_rotations / expectation with host arrays, host wall clock, max over ranks"},
             "gpu_launches": int(sum(v["launches"] for v in prof.values())) * world,
