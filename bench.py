@@ -376,14 +376,17 @@ def measure_e2e(wl, args, st):
     params = [wl["ra"] * (1.0 + 1e-3 * rng.normal()) for _ in range(args.steps + 1)]
     circuit.set_parameters(params[0])
     ham.expectation(circuit)  # warm-up (compiles the program)
+    st.transfer_bytes(reset=True)
     t0 = time.perf_counter()
     for k in range(args.steps):
         circuit.set_parameters(params[k + 1])
         ham.expectation(circuit)
     dt = (time.perf_counter() - t0) / args.steps
     rt._states.pop(n, None)
-    h2d = int(wl["rx"].size * 24 + wl["hx"].size * 24)
-    return {"value": 2.0 ** (n - 30) / dt, "unit": unit_for(n), "ms_per_step": 1e3 * dt, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 16,
+    h2d, d2h = (v // args.steps for v in st.transfer_bytes())  # counted by the library at every copy it issues
+    return {"value": 2.0 ** (n - 30) / dt, "unit": unit_for(n), "ms_per_step": 1e3 * dt, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "note": "the Hamiltonian's tiled plan (3.4 MB) is uploaded once and cached on the device by content hash; per step "
+                    "only the rotation tables, the per-launch kernel parameters and the energy cross the PCIe bus",
             "api": "Circuit.set_parameters(host array) + SymbolicHamiltonian.expectation(circuit) -> float"}  # fmt: skip
 
 

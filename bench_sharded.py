@@ -42,6 +42,7 @@ def main_sharded(args, n: int, nelec: int) -> None:
     local.profile_reset()
     local.profile_enable(True)
     ex.swap_seconds, ex.swap_bytes = 0.0, 0
+    local.transfer_bytes(reset=True)
     swaps0 = st.n_swaps
     clocks = ClockSampler(local_rank) if rank == 0 else None
     ex.barrier()
@@ -61,6 +62,7 @@ def main_sharded(args, n: int, nelec: int) -> None:
     dev_ms, wall_ms = float(t[0]), float(t[1])
     prof = local.profile()
     local.profile_enable(False)
+    h2d, d2h = local.transfer_bytes()
     clock_info = clocks.stop() if clocks else None
     swaps = st.n_swaps - swaps0
 
@@ -82,7 +84,7 @@ def main_sharded(args, n: int, nelec: int) -> None:
             "raw_evals_per_sec": 1e3 / ms_per_step, "energy": energies[-1], "energy_spread": float(np.ptp(energies)),
             "clocks": clock_info,
             "e2e": {"value": scale * 1e3 * args.steps / wall_ms, "unit": unit_for(n),
-                    "h2d_bytes_per_step": int(wl["rx"].size * 24 + wl["hx"].size * 24) * world, "d2h_bytes_per_step": 8 * world,
+                    "h2d_bytes_per_step": h2d // args.steps * world, "d2h_bytes_per_step": d2h // args.steps * world,
                     "api": "ShardedState.apply_pauli_rotations / expectation with host arrays, host wall clock, max over ranks"},
             "gpu_launches": int(sum(v["launches"] for v in prof.values())) * world,
             "roofline": {

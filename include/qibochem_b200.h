@@ -117,6 +117,9 @@ int qc_frequencies(qc_state* h, const uint64_t* samples, size_t n, int on_device
 /* Kernel classes: 0 K0 init, 1 K1 rotation pass, 2 K2 expectation sweeps, 3 reductions, 4 K5 sampling, 5 K3 shot
  * statistics, 6 K4 exchange, 7 K2 tiled expectation passes, 8 gradient sweeps.  Launch counts and algorithmic bytes are always accumulated; when enabled, every
  * launch is additionally bracketed by CUDA events on the handle's stream and its device time accumulated. */
+/* Host->device / device->host bytes the compute entry points (programs, tables, plans, kernel parameters, results,
+ * qc_copy_state_from_host) have moved since the last reset: bench.py's e2e.h2d_bytes_per_step / d2h_bytes_per_step. */
+int qc_transfer_bytes(qc_state* h, uint64_t* h2d_bytes, uint64_t* d2h_bytes, int reset);
 int qc_profile_enable(qc_state* h, int enabled);
 int qc_profile_reset(qc_state* h);
 int qc_profile_get(qc_state* h, int kernel_class, double* ms_total, uint64_t* launches, double* algorithmic_bytes);

@@ -39,6 +39,7 @@ SIGNATURES = {
     "qc_frequencies": (C.c_int, [_vp, _vp, C.c_size_t, C.c_int, C.c_uint64, _u64p, _i64p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "qc_profile_enable": (C.c_int, [_vp, C.c_int]),
     "qc_profile_reset": (C.c_int, [_vp]),
+    "qc_transfer_bytes": (C.c_int, [_vp, _u64p, _u64p, C.c_int]),
     "qc_profile_get": (C.c_int, [_vp, C.c_int, _f64p, _u64p, _f64p]),
     "qc_copy_state_to_host": (C.c_int, [_vp, _f64p, C.c_uint64, C.c_uint64]),
     "qc_copy_state_from_host": (C.c_int, [_vp, _f64p, C.c_uint64, C.c_uint64]),

@@ -83,6 +83,7 @@ struct qc_state {
     double* h_out = nullptr;       // pinned mirror of d_out
     double2* scratch_psi = nullptr;  // scratch copy of the shard (sampling), allocated lazily
     qc::Profiler prof;
+    uint64_t h2d_bytes = 0, d2h_bytes = 0;  // host<->device bytes moved by the product path since the last reset
     std::vector<qc::TiledPlan*> k2plans;  // cached plans of the tiled expectation (keyed by a hash of the term list; LRU)
     int k1_mode = 0;                  // 0 auto, 1 one HBM pass per fused run, 2 shared-memory tiles whenever a run fits
     int k2_mode = 0;                  // 0 auto, 1 force sweeps (one HBM pass per x-mask), 2 force tiles

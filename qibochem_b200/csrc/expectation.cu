@@ -183,6 +183,7 @@ static int run_sweeps(qc_state* h, size_t T, const uint64_t* xmask, const uint64
     memcpy(h->arena.host, groups.data(), bytes_groups);
     memcpy((char*)h->arena.host + off_terms, tdev.data(), bytes_terms);
     QC_CHECK(cudaMemcpyAsync(h->arena.dev, h->arena.host, off_terms + bytes_terms, cudaMemcpyHostToDevice, h->stream));
+    h->h2d_bytes += off_terms + bytes_terms;
     const XGroup* dgroups = (const XGroup*)h->arena.dev;
     const TermDev* dterms = (const TermDev*)((char*)h->arena.dev + off_terms);
 
@@ -235,6 +236,7 @@ extern "C" int qc_expectation(qc_state* h, size_t T, const uint64_t* xmask, cons
         tiled_plan_leftovers(plan, &lx, &lz, &lc, &nleft);
         if (nleft && run_sweeps(h, nleft, lx, lz, lc, false, 1, &ng)) return 1;
         QC_CHECK(cudaMemcpyAsync(h->h_out, h->d_out, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        h->d2h_bytes += 2 * sizeof(double);
         QC_CHECK(cudaStreamSynchronize(h->stream));
         *energy_out = h->h_out[0] + (nleft ? h->h_out[1] : 0.0);
         if (n_sweeps_out) *n_sweeps_out = passes + (int)ng;
@@ -245,6 +247,7 @@ extern "C" int qc_expectation(qc_state* h, size_t T, const uint64_t* xmask, cons
     if (run_sweeps(h, T, xmask, zmask, coeff, per_term != nullptr, 0, &ng)) return 1;
     if (per_term) {
         QC_CHECK(cudaMemcpyAsync(h->h_out, h->d_out, (ng + 1) * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        h->d2h_bytes += (ng + 1) * sizeof(double);
         QC_CHECK(cudaStreamSynchronize(h->stream));
         double e = 0.0;
         for (size_t k = 0; k < T; ++k) {
@@ -254,6 +257,7 @@ extern "C" int qc_expectation(qc_state* h, size_t T, const uint64_t* xmask, cons
         *energy_out = e;
     } else {
         QC_CHECK(cudaMemcpyAsync(h->h_out, h->d_out, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        h->d2h_bytes += sizeof(double);
         QC_CHECK(cudaStreamSynchronize(h->stream));
         *energy_out = h->h_out[0];
     }

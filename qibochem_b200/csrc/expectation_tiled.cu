@@ -320,6 +320,7 @@ int run_tiled_expectation(qc_state* h, size_t T, const uint64_t* xs, const uint6
         QC_REQUIRE(hp != nullptr, "qc_expectation: could not build the tiled plan");
         found = upload_plan(hp, hash);
         QC_REQUIRE(found != nullptr, "qc_expectation: could not upload the tiled plan");
+        h->h2d_bytes += hp->units.size() * sizeof(Unit16);
         if (h->k2plans.size() >= kMaxCachedPlans) {
             QC_CHECK(cudaStreamSynchronize(h->stream));  // the evicted plan may still be read by in-flight passes
             free_tiled_plan(h->k2plans.front());
@@ -344,6 +345,7 @@ int run_tiled_expectation(qc_state* h, size_t T, const uint64_t* xs, const uint6
         // the actual HBM traffic of this class is launches * 16 * dim
         {
             LaunchScope ls(h, kK2Tiled, 16.0 * (double)h->dim * (double)pass.n_groups);
+            h->h2d_bytes += sizeof(TPass);
             expectation_tiled_kernel<<<nb, kTileThreads, smem, h->stream>>>(h->psi, h->n, pass, plan->d_units,
                                                                           h->d_partials + p * nb);
         }

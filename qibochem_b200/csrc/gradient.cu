@@ -204,6 +204,7 @@ extern "C" int qc_energy_gradient(qc_state* h, size_t R, const uint64_t* rx, con
                 set_error("qc_energy_gradient: upload failed");
                 return 1;
             }
+            h->h2d_bytes += launch_groups.size() * sizeof(HGroup) + nt * sizeof(HTerm);
             // pageable host memory: the async copies above are staged synchronously, so the vectors may be reused
             {
                 LaunchScope ls(h, kGradient, 16.0 * (double)h->dim * (double)(launch_groups.size() + 2));
@@ -262,6 +263,7 @@ extern "C" int qc_energy_gradient(qc_state* h, size_t R, const uint64_t* rx, con
             return 1;
         }
     }
+    h->d2h_bytes += (2 + 2 * R) * sizeof(double);
     cudaError_t e = cudaMemcpyAsync(h->h_out, h->d_out, (2 + 2 * R) * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
     cleanup();

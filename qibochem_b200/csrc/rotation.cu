@@ -400,6 +400,7 @@ int apply_rotations_to(qc_state* h, double2* target, size_t R, const uint64_t* x
     }
     QC_CHECK(cudaMemcpyAsync(h->arena.dev, h->arena.host, total_entries * sizeof(double2), cudaMemcpyHostToDevice,
                              h->stream));
+    h->h2d_bytes += total_entries * sizeof(double2);
     const double2* dtab = (const double2*)h->arena.dev;
 
     const size_t tile_smem = (size_t)(kRotTileSize + kMaxBatchRuns * kTileRunTable) * sizeof(double2);
@@ -443,6 +444,7 @@ int apply_rotations_to(qc_state* h, double2* target, size_t R, const uint64_t* x
             QC_CHECK(cudaFuncSetAttribute(rot_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem));
             const uint64_t n_tiles = 1ull << (h->n - kRotTileBits);
             const int nb = (int)std::min<uint64_t>(n_tiles, (uint64_t)h->sm_count * 3);
+            h->h2d_bytes += sizeof(TileBatch);  // kernel parameters
             rot_tiled_kernel<<<nb, kRotTileThreads, tile_smem, h->stream>>>(target, h->n, tb, dtab);
             continue;
         }

@@ -237,6 +237,14 @@ int qc_set_option(qc_state* h, const char* key, int64_t value) {
     return 2;
 }
 
+int qc_transfer_bytes(qc_state* h, uint64_t* h2d_bytes, uint64_t* d2h_bytes, int reset) {
+    QC_REQUIRE(h, "qc_transfer_bytes: null handle");
+    if (h2d_bytes) *h2d_bytes = h->h2d_bytes;
+    if (d2h_bytes) *d2h_bytes = h->d2h_bytes;
+    if (reset) h->h2d_bytes = h->d2h_bytes = 0;
+    return 0;
+}
+
 int qc_profile_enable(qc_state* h, int enabled) {
     QC_REQUIRE(h, "qc_profile_enable: null handle");
     h->prof.enabled = enabled != 0;
@@ -282,6 +290,7 @@ int qc_copy_state_from_host(qc_state* h, const double* in, uint64_t offset, uint
     QC_REQUIRE(offset + count <= h->dim, "qc_copy_state_from_host: range out of bounds");
     QC_CHECK(cudaSetDevice(h->device));
     QC_CHECK(cudaMemcpyAsync(h->psi + offset, in, count * sizeof(double2), cudaMemcpyHostToDevice, h->stream));
+    h->h2d_bytes += count * sizeof(double2);
     QC_CHECK(cudaStreamSynchronize(h->stream));
     return 0;
 }

@@ -235,6 +235,12 @@ class DeviceState:
         """e.g. ``set_option("k2_mode", 1)``: 0 auto, 1 sweeps (one HBM pass per x-mask), 2 tiles."""
         _native.check(self._lib.qc_set_option(self._h, key.encode(), int(value)), "qc_set_option")
 
+    def transfer_bytes(self, reset: bool = False) -> tuple[int, int]:
+        """(host->device, device->host) bytes moved by the compute entry points since the last reset."""
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        _native.check(self._lib.qc_transfer_bytes(self._h, C.byref(a), C.byref(b), int(reset)), "qc_transfer_bytes")
+        return a.value, b.value
+
     def profile_enable(self, enabled: bool = True) -> None:
         _native.check(self._lib.qc_profile_enable(self._h, int(enabled)), "qc_profile_enable")
 
