@@ -113,6 +113,15 @@ int qc_parity_sums(qc_state* h, const uint64_t* samples, const int64_t* counts, 
 int qc_frequencies(qc_state* h, const uint64_t* samples, size_t n, int on_device, uint64_t keep_mask,
                    uint64_t* keys_out, int64_t* counts_out, size_t cap, size_t* n_unique_out);
 
+/* Squared deviations of a term group's value over the DISTINCT outcomes of a measurement (replaces the Python loop of
+ * sample_statistics, src/qibochem/measurement/result.py:150-155):  v_u = sum_j coeff[j] (-1)^{popcount(keys[u] & zmask[j])};
+ * sumsq_unweighted_out <- sum_u (v_u - mean)^2  (what the reference divides by n_shots - 1: every distinct outcome
+ * counted once), sumsq_weighted_out <- sum_u counts[u] (v_u - mean)^2  (the usual sample variance numerator).
+ * keys / counts / zmask / coeff are host arrays. */
+int qc_outcome_variance(qc_state* h, const uint64_t* keys, const int64_t* counts, size_t n_unique,
+                        const uint64_t* zmask, const double* coeff, size_t J, double mean, double* sumsq_unweighted_out,
+                        double* sumsq_weighted_out);
+
 /* ---- live profiler / launch counter (bench.py: roofline of the dominant kernel, gpu_launches) ----------------- */
 /* Kernel classes: 0 K0 init, 1 K1 rotation pass, 2 K2 expectation sweeps, 3 reductions, 4 K5 sampling, 5 K3 shot
  * statistics, 6 K4 exchange, 7 K2 tiled expectation passes, 8 gradient sweeps.  Launch counts and algorithmic bytes are always accumulated; when enabled, every

@@ -296,7 +296,46 @@ __global__ void __launch_bounds__(kThreads) histogram_hash_kernel(const uint64_t
     }
 }
 
+// Per distinct outcome u: v_u = sum_j c_j (-1)^{popc(key_u & m_j)};  partials[b] = sum_u (v_u - mean)^2,
+// partials[nb + b] = sum_u count_u (v_u - mean)^2 over CTA b's outcomes (fixed-order reduction: deterministic).
+constexpr int kVarTerms = 1024;
+__global__ void __launch_bounds__(kThreads) outcome_variance_kernel(const uint64_t* __restrict__ keys,
+                                                                    const int64_t* __restrict__ counts, size_t n_unique,
+                                                                    const uint64_t* __restrict__ masks,
+                                                                    const double* __restrict__ coeffs, uint32_t J,
+                                                                    double mean, double* __restrict__ partials) {
+    __shared__ uint64_t smask[kVarTerms];
+    __shared__ double scoef[kVarTerms];
+    const size_t stride = (size_t)gridDim.x * kThreads;
+    double acc_u = 0.0, acc_w = 0.0;
+    for (size_t u0 = (size_t)blockIdx.x * kThreads; u0 < n_unique; u0 += stride) {
+        const size_t u = u0 + threadIdx.x;
+        const uint64_t key = u < n_unique ? keys[u] : 0ull;
+        double v = 0.0;
+        for (uint32_t j0 = 0; j0 < J; j0 += kVarTerms) {
+            const uint32_t jn = min((uint32_t)kVarTerms, J - j0);
+            __syncthreads();
+            for (uint32_t j = threadIdx.x; j < jn; j += kThreads) smask[j] = masks[j0 + j], scoef[j] = coeffs[j0 + j];
+            __syncthreads();
+            for (uint32_t j = 0; j < jn; ++j) v += flip_sign(scoef[j], key, smask[j]);
+        }
+        if (u < n_unique) {
+            const double d = v - mean;
+            acc_u += d * d;
+            acc_w += (double)counts[u] * d * d;
+        }
+    }
+    const double tu = block_sum(acc_u);
+    const double tw = block_sum(acc_w);
+    if (threadIdx.x == 0) {
+        partials[blockIdx.x] = tu;
+        partials[gridDim.x + blockIdx.x] = tw;
+    }
+}
+
 }  // namespace qc
+
+
 
 extern "C" {
 
@@ -477,6 +516,46 @@ int qc_frequencies(qc_state* h, const uint64_t* samples, size_t n, int on_device
         counts_out[k] = found[k].second;
     }
     *n_unique_out = found.size();
+    return 0;
+}
+
+int qc_outcome_variance(qc_state* h, const uint64_t* keys, const int64_t* counts, size_t n_unique,
+                        const uint64_t* zmask, const double* coeff, size_t J, double mean, double* sumsq_unweighted_out,
+                        double* sumsq_weighted_out) {
+    using namespace qc;
+    QC_REQUIRE(h && sumsq_unweighted_out && sumsq_weighted_out, "qc_outcome_variance: null argument");
+    *sumsq_unweighted_out = *sumsq_weighted_out = 0.0;
+    if (n_unique == 0) return 0;
+    QC_REQUIRE(keys && counts && (J == 0 || (zmask && coeff)), "qc_outcome_variance: null array");
+    QC_REQUIRE(J < (1ull << 31), "qc_outcome_variance: too many terms");
+    QC_CHECK(cudaSetDevice(h->device));
+    const int nb = (int)std::min<size_t>((n_unique + kThreads - 1) / kThreads, (size_t)h->sm_count * 4);
+    if (h->ensure_partials((size_t)nb * 2) || h->ensure_out(2)) return 1;
+    void* staged = nullptr;
+    const size_t bytes = n_unique * 16 + J * 16;
+    QC_CHECK(cudaMalloc(&staged, std::max<size_t>(bytes, 16)));
+    uint64_t* dkeys = (uint64_t*)staged;
+    int64_t* dcounts = (int64_t*)(dkeys + n_unique);
+    uint64_t* dmasks = (uint64_t*)(dcounts + n_unique);
+    double* dcoef = (double*)(dmasks + J);
+    cudaError_t e = cudaMemcpyAsync(dkeys, keys, n_unique * 8, cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dcounts, counts, n_unique * 8, cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess && J) e = cudaMemcpyAsync(dmasks, zmask, J * 8, cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess && J) e = cudaMemcpyAsync(dcoef, coeff, J * 8, cudaMemcpyHostToDevice, h->stream);
+    h->h2d_bytes += bytes;
+    if (e == cudaSuccess) {
+        LaunchScope ls(h, kK3Shots, 16.0 * (double)n_unique);
+        outcome_variance_kernel<<<nb, kThreads, 0, h->stream>>>(dkeys, dcounts, n_unique, dmasks, dcoef, (uint32_t)J, mean,
+                                                                h->d_partials);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess && fold_partials(h, h->d_partials, 2, nb, nb, h->d_out)) e = cudaErrorUnknown;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h->h_out, h->d_out, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(staged);
+    QC_CHECK(e);
+    *sumsq_unweighted_out = h->h_out[0];
+    *sumsq_weighted_out = h->h_out[1];
     return 0;
 }
 

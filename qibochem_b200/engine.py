@@ -195,6 +195,21 @@ class DeviceState:
         del keep, ckeep
         return out
 
+    def outcome_variance(self, keys, counts, masks, coeffs, mean: float) -> tuple[float, float]:
+        """(sum_u (v_u - mean)^2, sum_u count_u (v_u - mean)^2) over distinct outcomes, v_u = sum_j c_j (-1)^{popc(key_u & m_j)}."""
+        k, m = _u64(keys), _u64(masks)
+        c = np.ascontiguousarray(np.asarray(counts, dtype=np.int64))
+        w = _f64(coeffs)
+        if k.shape != c.shape or m.shape != w.shape:
+            raise ValueError("keys/counts and masks/coeffs must have matching lengths")
+        a, b = C.c_double(0.0), C.c_double(0.0)
+        _native.check(
+            self._lib.qc_outcome_variance(self._h, _ptr(k, C.c_uint64), _ptr(c, C.c_int64), k.size, _ptr(m, C.c_uint64),
+                                          _ptr(w, C.c_double), m.size, C.c_double(float(mean)), C.byref(a), C.byref(b)),
+            "qc_outcome_variance",
+        )  # fmt: skip
+        return a.value, b.value
+
     def frequencies(self, samples, keep_mask: int):
         """Histogram of the samples restricted to ``keep_mask`` bits -> (keys ascending, counts)."""
         ptr, n, on_dev, keep = self._buf(samples)

@@ -1,3 +1,3 @@
-from qibochem_b200.measurement.result import expectation, expectation_from_samples
+from qibochem_b200.measurement.result import expectation, expectation_from_samples, sample_statistics, v_expectation
 
-__all__ = ["expectation", "expectation_from_samples"]
+__all__ = ["expectation", "expectation_from_samples", "sample_statistics", "v_expectation"]

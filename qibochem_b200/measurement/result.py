@@ -15,7 +15,7 @@ from collections import Counter
 import numpy as np
 
 from qibochem_b200.measurement.optimization import _measurement_basis_rotations
-from qibochem_b200.measurement.shot_allocation import allocate_shots
+from qibochem_b200.measurement.shot_allocation import allocate_shots, allocate_shots_by_variance
 from qibochem_b200.pauli import PauliSum
 from qibochem_b200.runtime import get_runtime
 
@@ -128,3 +128,79 @@ def expectation_from_samples(
         sums = state.parity_sums(samples, np.array(masks, dtype=np.uint64))
         total += float(np.dot(np.array(coeffs), sums / nshots))
     return total
+
+
+def _group_masks(expression: PauliSum, n: int):
+    """(coefficients, support masks in index-bit positions, constant) of a group expression."""
+    coeffs, masks, const = [], [], 0.0
+    for (x, z), c in expression.terms.items():
+        support = x | z
+        if support == 0:
+            const += complex(c).real
+            continue
+        m, q = 0, 0
+        while support >> q:
+            if (support >> q) & 1:
+                m |= 1 << (n - 1 - q)
+            q += 1
+        coeffs.append(complex(c).real)
+        masks.append(m)
+    return np.array(coeffs, dtype=np.float64), np.array(masks, dtype=np.uint64), const
+
+
+def sample_statistics(circuit, grouped_terms, n_shots: int = 1000, seed: int | None = None):
+    """Sample mean and sample variance of every term group from ``n_shots`` shots per group
+    (reference: ``src/qibochem/measurement/result.py:121-158``).
+
+    The reference's variance sums ``(value(outcome) - mean)^2`` over the DISTINCT measured outcomes -- every outcome
+    once, whatever its count -- and divides by ``n_shots - 1`` (result.py:150-155; its goldens,
+    ``tests/test_expectation_samples.py:139-155``, pin exactly that).  The same number is returned here; the state is
+    prepared once, and the per-outcome values and squared deviations are reduced on the device (K3).
+    """
+    from qibochem_b200.circuit import _next_seed
+
+    n = circuit.nqubits
+    state = circuit.run_on_device()
+    base_seed = _next_seed() if seed is None else int(seed)
+    means, variances = [], []
+    for i, (expression, measurement_gates, _rotation_gates) in enumerate(grouped_terms):
+        xb = sum(1 << (n - 1 - g.qubits[0]) for g in measurement_gates if g.basis[0] == "X")
+        yb = sum(1 << (n - 1 - g.qubits[0]) for g in measurement_gates if g.basis[0] == "Y")
+        keep = sum(1 << (n - 1 - g.qubits[0]) for g in measurement_gates)
+        samples = state.sample(xb, yb, n_shots, (base_seed + 0x9E3779B97F4A7C15 * (i + 1)) % (1 << 64), on_device=True)
+        coeffs, masks, const = _group_masks(expression, n)
+        sums = state.parity_sums(samples, masks)  # exact integers
+        mean = float(const + np.dot(coeffs, sums / n_shots))
+        # distinct outcomes over the measured qubits; keys come back compacted, so expand them to index-bit positions
+        keys, counts = state.frequencies(samples, keep)
+        kept_bits = [b for b in range(n) if (keep >> b) & 1]
+        full = np.zeros(keys.size, dtype=np.uint64)
+        for j, b in enumerate(kept_bits):
+            full |= ((keys >> np.uint64(j)) & np.uint64(1)) << np.uint64(b)
+        unweighted, _weighted = state.outcome_variance(full, counts, masks, coeffs, mean - const)
+        means.append(mean)
+        variances.append(unweighted / (n_shots - 1))
+    return means, variances
+
+
+def v_expectation(circuit, hamiltonian, n_shots: int, n_trial_shots: int, grouping: str | None = None, method: str = "vmsa") -> float:
+    """Expectation value with variance-based shot allocation (VMSA / VPSR; reference ``result.py:161-220``):
+    ``n_trial_shots`` per group give the sample variances, the remaining budget is split by
+    ``allocate_shots_by_variance`` and both estimates are combined weighted by their shot numbers."""
+    from qibochem_b200.hamiltonian import SymbolicHamiltonian
+
+    assert method in ("vmsa", "vpsr"), f"Unknown shot assignment method ({method}) called"
+    grouped_terms = _measurement_basis_rotations(hamiltonian, grouping=grouping)
+    assert (
+        n_trial_shots * len(grouped_terms) <= n_shots
+    ), f"n(Trial shots = {n_trial_shots}) * n(Term groups = {len(grouped_terms)}) > n(Total shots = {n_shots})"
+    sample_means, sample_variances = sample_statistics(circuit, grouped_terms, n_shots=n_trial_shots)
+    remaining = allocate_shots_by_variance(n_shots, n_trial_shots, sample_variances, method=method)
+    total = 0.0
+    for (expression, _, _), mean0, extra in zip(grouped_terms, sample_means, remaining):
+        new_mean = 0.0
+        if extra:
+            sub = SymbolicHamiltonian(expression, nqubits=hamiltonian.nqubits)
+            new_mean = expectation_from_samples(circuit, sub, n_shots=extra, grouping=grouping)
+        total += (n_trial_shots * mean0 + extra * new_mean) / (n_trial_shots + extra)
+    return total + _constant_term(hamiltonian)

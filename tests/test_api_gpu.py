@@ -323,3 +323,88 @@ def test_adjoint_gradient_equals_parameter_shift_on_uccsd():
         assert grad[k] == pytest.approx(parameter_shift(circuit, ham, k), abs=1e-9)
     with pytest.raises(ValueError):
         parameter_shift(circuit, ham, grad.size)
+
+
+@pytest.mark.parametrize(
+    "terms,grouping,expected_means,expected_variances",
+    [
+        ("X0", None, [1.0], [0.0]),
+        ("X0 + Z0", None, [1.0, 0.0], [0.0, 0.0]),
+        ("Z0 + X0*Z1", "qwc", [-1.0, 0.0], [0.0, 0.0]),
+    ],
+)
+def test_sample_statistics(terms, grouping, expected_means, expected_variances):
+    """tests/test_expectation_samples.py:139-155 of the reference (same circuit, shots and tolerances)."""
+    A = _api()
+    from qibochem_b200.measurement import sample_statistics
+    from qibochem_b200.measurement.optimization import _measurement_basis_rotations
+
+    X, Z = A["X"], A["Z"]
+    form = {"X0": X(0), "X0 + Z0": X(0) + Z(0), "Z0 + X0*Z1": Z(0) + X(0) * Z(1)}[terms]
+    ham = A["SymbolicHamiltonian"](form, nqubits=2)
+    circuit = A["Circuit"](2)
+    circuit.add(A["gates"].H(0))
+    circuit.add(A["gates"].X(1))
+    grouped = _measurement_basis_rotations(ham, grouping)
+    means, variances = sample_statistics(circuit, grouped, n_shots=20000)
+    order = np.argsort(means)  # group order is not part of the contract
+    assert sorted(means) == pytest.approx(sorted(expected_means), abs=0.08)
+    assert [variances[k] for k in order] == pytest.approx([0.0] * len(means), abs=0.1)
+
+
+def test_sample_statistics_matches_reference_formula_on_identical_samples():
+    """The device reduction equals a plain restatement of result.py:144-155 on the same samples: mean from the
+    frequencies, sum over DISTINCT outcomes of (value - mean)^2, divided by n_shots - 1."""
+    A = _api()
+    from collections import Counter
+
+    from qibochem_b200.measurement import sample_statistics
+    from qibochem_b200.measurement.optimization import _measurement_basis_rotations
+    from qibochem_b200.measurement.result import _group_masks
+
+    X, Y, Z = A["X"], A["Y"], A["Z"]
+    n = 5
+    ham = A["SymbolicHamiltonian"](0.7 * Z(0) * Z(3) + 0.2 * X(1) * Z(2) - 1.1 * X(1) * Z(4) + 0.4 * Y(0) * Y(2) + 0.9 * Z(2), nqubits=n)
+    g = A["gates"]
+    circuit = A["Circuit"](n)
+    circuit.add(g.RX(q, 0.3 + 0.2 * q) for q in range(n))
+    circuit.add(g.CNOT(q, q + 1) for q in range(n - 1))
+    circuit.add(g.RY(q, 0.5 - 0.1 * q) for q in range(n))
+    grouped = _measurement_basis_rotations(ham, "qwc")
+    nshots, seed = 5000, 1234
+    means, variances = sample_statistics(circuit, grouped, n_shots=nshots, seed=seed)
+    st = circuit.run_on_device()
+    for i, (expr, m_gates, _) in enumerate(grouped):
+        xb = sum(1 << (n - 1 - gt.qubits[0]) for gt in m_gates if gt.basis[0] == "X")
+        yb = sum(1 << (n - 1 - gt.qubits[0]) for gt in m_gates if gt.basis[0] == "Y")
+        samples = st.sample(xb, yb, nshots, (seed + 0x9E3779B97F4A7C15 * (i + 1)) % (1 << 64))
+        coeffs, masks, const = _group_masks(expr, n)
+        keep = sum(1 << (n - 1 - gt.qubits[0]) for gt in m_gates)
+        freq = Counter((samples & np.uint64(keep)).tolist())
+        value = lambda key: const + sum(c * (-1) ** bin(key & int(m)).count("1") for c, m in zip(coeffs, masks))  # noqa: E731
+        ref_mean = sum(value(k) * c for k, c in freq.items()) / nshots
+        ref_var = sum((value(k) - ref_mean) ** 2 for k in freq) / (nshots - 1)
+        assert means[i] == pytest.approx(ref_mean, abs=1e-12)
+        assert variances[i] == pytest.approx(ref_var, abs=1e-12)
+
+
+@pytest.mark.parametrize("grouping", [None, "qwc"])
+def test_v_expectation_vmsa(grouping):
+    """tests/test_expectation_samples.py:158-185 of the reference (qwc instead of gc)."""
+    A = _api()
+    from qibochem_b200.measurement import v_expectation
+
+    X, Y, Z = A["X"], A["Y"], A["Z"]
+    g = A["gates"]
+    for form in (0.2 * X(0) + Y(2) + 13.0, Y(0) + Z(1) + X(0) * Z(2)):
+        ham = A["SymbolicHamiltonian"](form, nqubits=3)
+        circuit = A["Circuit"](3)
+        circuit.add(g.RX(i, 0.1 * i) for i in range(3))
+        circuit.add(g.CNOT(i, i + 1) for i in range(2))
+        circuit.add(g.RZ(i, 0.2 * i) for i in range(3))
+        expected = ham.expectation(circuit)
+        for method in ("vmsa", "vpsr"):
+            got = v_expectation(circuit, ham, n_trial_shots=2000, n_shots=50000, grouping=grouping, method=method)
+            assert got == pytest.approx(expected, abs=0.08)
+    with pytest.raises(AssertionError):
+        v_expectation(circuit, ham, n_trial_shots=2000, n_shots=10, grouping=grouping)
