@@ -109,6 +109,9 @@ class ShardedState:
 
     # ---- K0 ---------------------------------------------------------------------------------------------------
     def set_basis_state(self, index: int) -> None:
+        # The state is rewritten, so the bit permutation can be reset for free: every energy evaluation then walks
+        # through the SAME sequence of layouts and the device-side plans of the local shard are reused.
+        self.pos = list(range(self.n))
         loc, glob = self._to_physical(index)
         self.local.set_basis_state(loc, has_one=(glob == self.rank))
 
