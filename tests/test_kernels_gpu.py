@@ -488,3 +488,32 @@ def test_adjoint_gradient_matches_parameter_shift_oracle(DeviceState, n):
         # and the tiled / sweep expectation agrees with <psi|H psi> of the adjoint pass
         st.apply_pauli_rotations(xs, zs, phis)
         assert abs(st.expectation(hx, hz, hc) - e) < E_TOL
+
+
+@pytest.mark.parametrize("n,seed", [(12, 0), (14, 1), (15, 2)])
+def test_tiled_expectation_random_dense_hamiltonian(DeviceState, n, seed):
+    """Unstructured term lists: random x-masks of every weight 0..7 with random z-masks, large same-x groups with
+    many distinct z (pattern sums + LIN entries, split blobs), duplicates; tiles == oracle."""
+    from oracle import oracle_c as OC
+
+    rng = np.random.default_rng(seed)
+    xs, zs = [], []
+    for _ in range(2500):
+        w = int(rng.integers(0, 8))
+        x = int(sum(1 << int(b) for b in rng.choice(n, size=w, replace=False)))
+        xs.append(x), zs.append(int(rng.integers(0, 2**n)))
+    for x in (0, 0b11, 0b10110, (1 << (n - 1)) | 1):  # big groups: >> 300 distinct z per x-mask
+        for z in rng.choice(2**n, size=900, replace=False):
+            xs.append(x), zs.append(int(z))
+    xs += xs[:50]
+    zs += zs[:50]  # duplicated terms simply add up
+    cs = rng.normal(size=len(xs))
+    psi = random_state(n, 99 + seed)
+    ref = OC.expectation_masks(psi, n, xs, zs, cs)
+    with DeviceState(n) as st:
+        st.from_numpy(psi)
+        st.set_option("k2_mode", 2)
+        e = st.expectation(xs, zs, cs)
+        assert abs(e - ref) < 1e-9 * max(1.0, np.abs(cs).sum() / 50)
+        st.set_option("k2_mode", 1)
+        assert abs(st.expectation(xs, zs, cs) - e) < 1e-9 * max(1.0, np.abs(cs).sum() / 50)
