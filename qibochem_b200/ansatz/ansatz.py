@@ -101,20 +101,22 @@ def circuit_ansatz(
     include_hf: bool = True,
     **kwargs,
 ) -> Circuit:
-    """Parameterised ansatz circuit for a molecule.  ``"ucc"`` is the B200 hot path; the other ansatz families of
-    the reference (qeb, givens, br, symm, ham) are not Pauli-rotation programs and are outside this package.
+    """Parameterised ansatz circuit for a molecule.  ``"ucc"`` is the B200 hot path; ``"qeb"`` and ``"givens"`` are
+    the same kind of program (fused runs of commuting Pauli rotations); the other ansatz families of the reference
+    (br, symm, ham) are outside this package.
 
     Args:
         molecule: object with ``nso``, ``nelec``, ``n_active_orbs``, ``n_active_e``, ``eps``, ``tei``
-        ansatz: ``"ucc"``
+        ansatz: ``"ucc"``, ``"qeb"`` or ``"givens"``
         excitations: fermionic excitations; default: all doubles, then all singles (reference order)
         thetas: one parameter per excitation; default: MP2 amplitudes
         include_hf: start from the Hartree-Fock state
     """
-    if ansatz in ("qeb", "givens", "br", "symm", "ham"):
+    if ansatz in ("br", "symm", "ham"):
         raise NotImplementedError(f'ansatz "{ansatz}" is outside the B200 hot path (only "ucc" is built)')
-    if ansatz != "ucc":
+    if ansatz not in ("ucc", "qeb", "givens"):
         raise ValueError('Invalid argument for "ansatz"')
+    builder = {"ucc": ucc_circuit, "qeb": qeb_circuit, "givens": givens_circuit}[ansatz]
     nqubits = molecule.nso if molecule.n_active_orbs is None else molecule.n_active_orbs
     nelec = molecule.nelec if molecule.n_active_e is None else molecule.n_active_e
 
@@ -134,5 +136,48 @@ def circuit_ansatz(
     if include_hf:
         circuit += hf_circuit(nqubits, nelec, **kwargs)
     for excitation, theta in zip(excitations, thetas):
-        circuit += ucc_circuit(nqubits, excitation, theta, **kwargs)
+        circuit += builder(nqubits, excitation, theta, **kwargs)
+    return circuit
+
+
+def _check_excitation(excitation):
+    n_orbitals = len(excitation)
+    if not n_orbitals:
+        raise ValueError("No excitations given")
+    if n_orbitals % 2 != 0:
+        raise ValueError(f"{excitation} must have an even number of items")
+    return n_orbitals
+
+
+def qeb_circuit(nqubits: int, excitation: Sequence[int], theta: float = 0.0, **kwargs) -> Circuit:
+    """Qubit-excitation-based circuit of ONE excitation (reference: ``ansatz.py:353-398``; JW only).
+
+    Same gate sequence as the reference -- a CNOT/X fan-in, one multi-controlled RY(2 theta), the fan-in reversed --
+    but the controlled rotation is 2^k commuting Pauli rotations sharing one x-mask (one device pass), and the single
+    trainable parameter is still the RY angle."""
+    _check_excitation(excitation)
+    n_tuples = len(excitation) // 2
+    i_array, a_array = list(excitation[:n_tuples]), list(excitation[n_tuples:])
+    fwd = [gates.CNOT(i_array[-1], i) for i in i_array[-2::-1]]
+    fwd += [gates.CNOT(a_array[-1], a) for a in a_array[-2::-1]]
+    fwd.append(gates.CNOT(a_array[-1], i_array[-1]))
+    fwd += [gates.X(q) for q in excitation if q not in (i_array[-1], a_array[-1])]
+    circuit = Circuit(nqubits, **kwargs)
+    circuit.add(fwd)
+    circuit.add(gates.RY(a_array[-1], 2.0 * theta).controlled_by(*excitation[:-1]))
+    circuit.add(fwd[::-1])
+    return circuit
+
+
+def givens_circuit(nqubits: int, excitation: Sequence[int], theta: float = 0.0, **kwargs) -> Circuit:
+    """Fermionic excitation as a Givens rotation (reference: ``ansatz.py:401-435``): ``GIVENS`` for two orbitals,
+    ``GeneralizedRBS(in, out, -theta)`` otherwise; each is one fused run of commuting Pauli rotations here."""
+    n_orbitals = _check_excitation(excitation)
+    orbitals = sorted(excitation)
+    q_in, q_out = orbitals[: n_orbitals // 2], orbitals[n_orbitals // 2 :]
+    circuit = Circuit(nqubits, **kwargs)
+    if n_orbitals == 2:
+        circuit.add(gates.GIVENS(q_in[0], q_out[0], theta))
+    else:
+        circuit.add(gates.GeneralizedRBS(q_in, q_out, -theta))
     return circuit

@@ -184,6 +184,26 @@ class _ParamRotation(Gate):
     def dagger(self):
         return type(self)(self.qubits[0], -self.parameters[0])
 
+    def controlled_by(self, *controls: int) -> "Gate":
+        """Multi-controlled rotation (qibo's ``gate.controlled_by``; the reference uses it for the MCRY of
+        ``qeb_circuit``, ``src/qibochem/ansatz/ansatz.py:395``).  With projectors (1 - Z_c)/2 on the controls,
+        ``C^k-R_P(theta) = prod_S exp(-i theta (-1)^{|S|} / 2^k  Z_S P_t / 2)`` over the subsets S of the controls: 2^k
+        commuting strings that share one x-mask, i.e. ONE fused pass on the device."""
+        if not controls:
+            return self
+        t = self.qubits[0]
+        if t in controls or len(set(controls)) != len(controls):
+            raise ValueError("control and target qubits must be distinct")
+        k = len(controls)
+        strings, coeffs = [], []
+        for subset in range(1 << k):
+            zs = [controls[j] for j in range(k) if (subset >> j) & 1]
+            strings.append(" ".join([f"Z{q}" for q in zs] + [f"{self.letter}{t}"]))
+            coeffs.append((-1.0) ** len(zs) / (1 << k))
+        gate = PauliRotationSum(strings, coeffs, self.parameters[0], name=f"c{self.name}")
+        gate.qubits = tuple(controls) + (t,)
+        return gate
+
 
 class RX(_ParamRotation):
     name = "rx"
@@ -231,6 +251,112 @@ class PauliRotation(Gate):
 
     def __repr__(self):
         return f"exp(-i*{self.parameters[0]}/2 * [{self.pauli_string}])"
+
+
+class PauliRotationSum(Gate):
+    """``exp(-i theta/2 * sum_j c_j P_j)`` for MUTUALLY COMMUTING Pauli strings with one shared parameter theta:
+    lowers to one rotation per string with angle ``c_j * theta``.  Building block of the controlled rotations, the
+    Givens / RBS gates and the qubit-excitation (QEB) circuits; strings that also share their x-mask fuse into a
+    single device pass."""
+
+    name = "pauli_rotation_sum"
+    n_params = 1
+
+    def __init__(self, strings, coeffs, theta=0.0, name: str | None = None):
+        strings = [" ".join(sorted(s.split(), key=lambda o: int(o[1:]))) for s in strings]
+        coeffs = [float(c) for c in coeffs]
+        if len(strings) != len(coeffs) or not strings:
+            raise ValueError("one real coefficient per Pauli string expected")
+        masks = [string_to_masks(s) for s in strings]
+        for i, (x1, z1) in enumerate(masks):
+            for x2, z2 in masks[i + 1 :]:
+                if (bin(x1 & z2).count("1") + bin(z1 & x2).count("1")) & 1:
+                    raise ValueError("PauliRotationSum needs mutually commuting strings")
+        qubits = sorted({int(o[1:]) for s in strings for o in s.split()})
+        super().__init__(*qubits)
+        self.strings, self.coeffs = strings, coeffs
+        self.parameters = (theta,)
+        if name:
+            self.name = name
+
+    @property
+    def target_qubits(self):
+        return self.qubits
+
+    @property
+    def control_qubits(self):
+        return ()
+
+    def lower(self):
+        theta = _real(self.parameters[0])
+        return [self._rot(s, c * theta, 0, c) for s, c in zip(self.strings, self.coeffs)], 1.0
+
+    def dagger(self):
+        out = PauliRotationSum(self.strings, self.coeffs, -self.parameters[0], name=self.name)
+        out.qubits = self.qubits
+        return out
+
+    def __repr__(self):
+        return f"{self.name}({', '.join(map(str, self.qubits))}, {self.parameters[0]})"
+
+
+def _subspace_rotation_generator(qubits_in, qubits_out):
+    """Pauli expansion of the Hermitian G with ``exp(-i theta G) = exp(theta (K - K^dagger))``,
+    ``K = |in = 0..0, out = 1..1><in = 1..1, out = 0..0|``: the rotation that takes ``|1..1, 0..0>`` to
+    ``cos(theta)|1..1, 0..0> + sin(theta)|0..0, 1..1>`` and leaves every other basis state alone.
+    Returns (strings, real coefficients)."""
+    from qibochem_b200.pauli import PauliSum, masks_to_string
+
+    lower = lambda q: (PauliSum.from_string(f"X{q}") + PauliSum.from_string(f"Y{q}", 1j)) * 0.5  # noqa: E731  |0><1|
+    raise_ = lambda q: (PauliSum.from_string(f"X{q}") + PauliSum.from_string(f"Y{q}", -1j)) * 0.5  # noqa: E731  |1><0|
+    K = PauliSum.identity()
+    for q in qubits_in:
+        K = K * lower(q)
+    for q in qubits_out:
+        K = K * raise_(q)
+    A = K - K.dagger()  # anti-Hermitian:  A = -i G
+    strings, coeffs = [], []
+    for (x, z), c in A.terms.items():
+        g = 1j * complex(c)  # G = i A
+        if abs(g) < 1e-14:
+            continue
+        if abs(g.imag) > 1e-12:
+            raise RuntimeError("internal error: generator is not Hermitian")
+        strings.append(masks_to_string(x, z))
+        coeffs.append(g.real)
+    return strings, coeffs
+
+
+class GIVENS(PauliRotationSum):
+    """qibo's ``gates.GIVENS(q0, q1, theta)`` [recalled: qibo is not installable here]: identity on |00>, |11> and
+    ``[[cos, -sin], [sin, cos]]`` on (|01>, |10>).  Used by ``givens_circuit`` (``ansatz.py:430``)."""
+
+    def __init__(self, q0: int, q1: int, theta=0.0):
+        strings, coeffs = _subspace_rotation_generator([q0], [q1])
+        # exp(-i theta G) takes |q0 = 1, q1 = 0> to cos|10> + sin|01>; qibo's matrix takes |10> to -sin|01> + cos|10>
+        super().__init__(strings, [-2.0 * c for c in coeffs], theta, name="givens")
+        self.qubits = (int(q0), int(q1))
+
+    def dagger(self):
+        return GIVENS(self.qubits[0], self.qubits[1], -self.parameters[0])
+
+
+class GeneralizedRBS(PauliRotationSum):
+    """qibo's ``gates.GeneralizedRBS(qubits_in, qubits_out, theta)`` with phi = 0 [recalled]: the rotation
+    ``[[cos, -sin], [sin, cos]]`` on (``|in = 1..1, out = 0..0>``, ``|in = 0..0, out = 1..1>``), identity elsewhere.
+    Used by ``givens_circuit`` for double excitations (``ansatz.py:432``)."""
+
+    def __init__(self, qubits_in, qubits_out, theta=0.0, phi=0.0):
+        if phi:
+            raise NotImplementedError("GeneralizedRBS with phi != 0 is outside the hot path")
+        qubits_in, qubits_out = [int(q) for q in qubits_in], [int(q) for q in qubits_out]
+        strings, coeffs = _subspace_rotation_generator(qubits_in, qubits_out)
+        super().__init__(strings, [2.0 * c for c in coeffs], theta, name="grbs")
+        self.qubits_in, self.qubits_out = tuple(qubits_in), tuple(qubits_out)
+        self.qubits = self.qubits_in + self.qubits_out
+
+    def dagger(self):
+        return GeneralizedRBS(self.qubits_in, self.qubits_out, -self.parameters[0])
 
 
 class M(Gate):

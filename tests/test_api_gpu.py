@@ -408,3 +408,83 @@ def test_v_expectation_vmsa(grouping):
             assert got == pytest.approx(expected, abs=0.08)
     with pytest.raises(AssertionError):
         v_expectation(circuit, ham, n_trial_shots=2000, n_shots=10, grouping=grouping)
+
+
+def _mcry_matrix(k, phi):
+    """RY(phi) on the last of k+1 qubits, controlled on the first k being 1 (qubit 0 = most significant)."""
+    dim = 2 ** (k + 1)
+    m = np.eye(dim, dtype=complex)
+    c, s = np.cos(phi / 2), np.sin(phi / 2)
+    m[dim - 2 :, dim - 2 :] = [[c, -s], [s, c]]
+    return m
+
+
+@pytest.mark.parametrize("excitation", [[0, 2], [1, 3], [0, 1, 2, 3], [3, 0, 4, 1]])
+def test_qeb_circuit_equals_reference_gate_sequence(excitation):
+    """qeb_circuit == the gate list of the reference (ansatz.py:384-397: CNOT/X fan-in, multi-controlled RY(2 theta),
+    fan-in reversed) executed gate by gate in the oracle, on a random state; one trainable parameter (the RY angle)."""
+    A = _api()
+    from qibochem_b200.ansatz import qeb_circuit
+
+    n, theta = 5, 0.3173
+    rng = np.random.default_rng(len(excitation) + excitation[0])
+    psi = rng.normal(size=2**n) + 1j * rng.normal(size=2**n)
+    psi /= np.linalg.norm(psi)
+    k = len(excitation) // 2
+    i_arr, a_arr = excitation[:k], excitation[k:]
+    fwd = [("CNOT", (i_arr[-1], i), None) for i in i_arr[-2::-1]]
+    fwd += [("CNOT", (a_arr[-1], a), None) for a in a_arr[-2::-1]]
+    fwd.append(("CNOT", (a_arr[-1], i_arr[-1]), None))
+    fwd += [("X", (q,), None) for q in excitation if q not in (i_arr[-1], a_arr[-1])]
+    ref = O.run_gates(n, fwd, state=psi.copy())
+    ref = O.apply_gate(ref, n, _mcry_matrix(len(excitation) - 1, 2 * theta), list(excitation[:-1]) + [a_arr[-1]])
+    ref = O.run_gates(n, fwd[::-1], state=ref)
+    circuit = qeb_circuit(n, excitation, theta)
+    assert len(circuit.get_parameters()) == 1 and circuit.get_parameters()[0][0] == pytest.approx(2 * theta)
+    got = circuit(initial_state=psi).state()
+    assert np.abs(got - ref).max() < 1e-12
+    # the excitation moves |i..=1, a..=0> towards |i..=0, a..=1> and leaves the vacuum alone (tests/test_ansatz.py:208-212)
+    vac = qeb_circuit(n, excitation, theta)().state()
+    assert abs(vac[0] - 1.0) < 1e-12
+    with pytest.raises(ValueError):
+        qeb_circuit(n, [0, 1, 2])
+    with pytest.raises(ValueError):
+        qeb_circuit(n, [])
+
+
+def test_givens_circuit_and_gates():
+    """GIVENS / GeneralizedRBS as fused Pauli-rotation runs: the documented matrices [recalled from qibo], and the
+    reference's own check (tests/test_ansatz.py:284-300): equal to the paper's CNOT/RY/H decomposition on |0000>."""
+    A = _api()
+    from qibochem_b200.ansatz import givens_circuit
+
+    g, n, theta = A["gates"], 4, 0.27183
+    c, s = np.cos(theta), np.sin(theta)
+    for q0, q1 in ((0, 2), (3, 1)):
+        circ = A["Circuit"](n)
+        circ.add(g.GIVENS(q0, q1, theta))
+        for b0, b1, expect in ((0, 1, {(0, 1): c, (1, 0): s}), (1, 0, {(0, 1): -s, (1, 0): c}), (1, 1, {(1, 1): 1.0}), (0, 0, {(0, 0): 1.0})):
+            e0 = np.zeros(2**n, dtype=complex)
+            e0[(b0 << (n - 1 - q0)) | (b1 << (n - 1 - q1))] = 1.0
+            out = circ(initial_state=e0).state()
+            want = np.zeros(2**n, dtype=complex)
+            for (c0, c1), v in expect.items():
+                want[(c0 << (n - 1 - q0)) | (c1 << (n - 1 - q1))] = v
+            assert np.abs(out - want).max() < 1e-12
+    # double excitation through GeneralizedRBS(in, out, -theta): rotation between |1100> and |0011> only
+    circ = givens_circuit(n, [0, 1, 2, 3], theta)
+    assert len(circ.get_parameters()) == 1
+    e0 = np.zeros(2**n, dtype=complex)
+    e0[0b1100] = 1.0
+    out = circ(initial_state=e0).state()
+    assert abs(out[0b1100] - c) < 1e-12 and abs(abs(out[0b0011]) - abs(s)) < 1e-12 and abs(np.linalg.norm(out) - 1) < 1e-12
+    for excitation in ([0, 2], [0, 1, 2, 3]):
+        vac = givens_circuit(n, excitation, theta)().state()
+        assert abs(vac[0] - 1.0) < 1e-12 and np.abs(vac[1:]).max() < 1e-12
+    with pytest.raises(ValueError):
+        givens_circuit(n, [0, 1, 2])
+    # the whole run fuses into ONE device pass per excitation
+    from qibochem_b200.runtime import get_runtime
+
+    circ.run_on_device()
+    assert get_runtime().state(n).last_passes == 1
