@@ -133,6 +133,8 @@ __device__ __forceinline__ unsigned sign_parity(uint64_t base, uint32_t org, con
 // One CTA = 128 threads, 64 KB tile + the pass's blob (sub-cube headers + records, <= 44 KB) in shared memory;
 // 2 CTAs per SM.  Everything the inner loops read besides the amplitudes comes from shared memory (broadcast LDS)
 // or the constant bank (TPass), so no global-load latency sits on the critical path.
+// GENERIC = false: the pass holds simple quads only (the common case) and the record loop is compiled out.
+template <bool GENERIC>
 __global__ void __launch_bounds__(kTileThreads, 2)
     expectation_tiled_kernel(const double2* __restrict__ psi, int n, const TPass pass, const uint4* __restrict__ units,
                              double* __restrict__ partials) {
@@ -178,15 +180,10 @@ __global__ void __launch_bounds__(kTileThreads, 2)
         for (uint32_t rb = 0; rb < pass.n_rblocks; ++rb) {
             const uint4 b0 = blob[rb * kRBlockUnits];      // sbit[0..4], perm[0..5]
             const uint4 b1 = blob[rb * kRBlockUnits + 1];  // perm[6], pad, rec_off, n_recs, n_groups
-            // tile-local origin of this thread's sub-cube: thread bit j -> position perm[j]
-            uint32_t org = 0;
-            {
-                const uint32_t pm[7] = {(b0.z >> 16) & 0xffu, b0.z >> 24, b0.w & 0xffu, (b0.w >> 8) & 0xffu,
-                                        (b0.w >> 16) & 0xffu, b0.w >> 24, b1.x & 0xffu};
-#pragma unroll
-                for (int j = 0; j < 7; ++j) org |= ((threadIdx.x >> j) & 1u) << pm[j];
-            }
-            const uint32_t org_sw = k2_swizzle(org);
+            // tile-local origin of this thread's sub-cube (and its swizzled slot) from the visit's two origin tables
+            const uint32_t* otab = reinterpret_cast<const uint32_t*>(blob + rb * kRBlockUnits + 2);
+            const uint32_t packed = otab[threadIdx.x & 15u] ^ otab[16u + (threadIdx.x >> 4)];
+            const uint32_t org = packed >> 16, org_sw = packed & 0xffffu;
             const uint32_t sb0 = b0.x & 0xffffu, sb1 = b0.x >> 16, sb2 = b0.y & 0xffffu, sb3 = b0.y >> 16, sb4 = b0.z & 0xffffu;
             double2 a[32];
 #pragma unroll
@@ -216,7 +213,7 @@ __global__ void __launch_bounds__(kTileThreads, 2)
 #undef QC_QUAD
             // ---- generic records
             double A0 = 0.0, A1 = 0.0, A2 = 0.0, A3 = 0.0;
-            for (uint32_t r = 0; r < b1.z; ++r) {
+            for (uint32_t r = 0; GENERIC && r < b1.z; ++r) {
                 const uint4 hd = *rp;
                 const uint32_t meta = hd.w;
                 const uint32_t kind = meta_kind(meta);
@@ -332,9 +329,10 @@ int run_tiled_expectation(qc_state* h, size_t T, const uint64_t* xs, const uint6
     const HostPlan* hp = plan->host;
     const size_t smem = (size_t)kTileSize * sizeof(double2) + (size_t)kBlobCapUnits * 16;
     const int ctas = 2;
-    QC_CHECK(cudaFuncSetAttribute(expectation_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    QC_CHECK(cudaFuncSetAttribute(expectation_tiled_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                  cudaSharedmemCarveoutMaxShared));
+    for (auto kernel : {expectation_tiled_kernel<true>, expectation_tiled_kernel<false>}) {
+        QC_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        QC_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    }
     const uint64_t n_tiles = 1ull << (h->n - kTileBits);
     const int nb = (int)std::min<uint64_t>(n_tiles, (uint64_t)h->sm_count * ctas);
     const size_t np = hp->passes.size();
@@ -346,8 +344,8 @@ int run_tiled_expectation(qc_state* h, size_t T, const uint64_t* xs, const uint6
         {
             LaunchScope ls(h, kK2Tiled, 16.0 * (double)h->dim * (double)pass.n_groups);
             h->h2d_bytes += sizeof(TPass);
-            expectation_tiled_kernel<<<nb, kTileThreads, smem, h->stream>>>(h->psi, h->n, pass, plan->d_units,
-                                                                          h->d_partials + p * nb);
+            auto kernel = pass.n_generic ? expectation_tiled_kernel<true> : expectation_tiled_kernel<false>;
+            kernel<<<nb, kTileThreads, smem, h->stream>>>(h->psi, h->n, pass, plan->d_units, h->d_partials + p * nb);
         }
         QC_CHECK(cudaGetLastError());
     }

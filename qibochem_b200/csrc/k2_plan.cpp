@@ -416,10 +416,20 @@ HostPlan* build_host_plan(int n, size_t T, const uint64_t* xs, const uint64_t* z
             pass.n_groups = cur_groups;
             uint32_t rec_off = (uint32_t)cur.size() * kRBlockUnits;
             for (RB& rb : cur) {
+                pass.n_generic += rb.hdr.n_recs;
                 rb.hdr.rec_off = rec_off;
                 rec_off += (uint32_t)rb.recs.size();
                 for (int j = 0; j < kRBits; ++j) rec_off += (uint32_t)rb.quads[j].size();
                 push_units(plan->units, &rb.hdr, sizeof(TRBlock));
+                uint32_t origin[24];  // lo[16] from thread bits 0..3, hi[8] from thread bits 4..6
+                for (uint32_t t = 0; t < 24; ++t) {
+                    const uint32_t bits = t < 16 ? t : (t - 16) << 4;
+                    uint32_t org = 0;
+                    for (int j = 0; j < kTileBits - kRBits; ++j)
+                        if ((bits >> j) & 1u) org |= 1u << rb.hdr.perm[j];
+                    origin[t] = (org << 16) | k2_swizzle(org);
+                }
+                push_units(plan->units, origin, sizeof(origin));
             }
             for (RB& rb : cur) {
                 for (int j = 0; j < kRBits; ++j)

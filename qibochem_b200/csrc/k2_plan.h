@@ -37,9 +37,11 @@ struct TPass {             // kernel parameter (constant bank)
     uint32_t blob_units;   // <= kBlobCapUnits
     uint32_t n_rblocks;
     uint32_t n_groups;     // x-masks served by this pass
+    uint32_t n_generic;    // records outside the straight-line quad path (0: the lean kernel variant runs the pass)
+    uint32_t pad;
 };
 
-struct TRBlock {           // 32 bytes = 2 units
+struct TRBlock {           // 32 bytes = 2 units, followed by 6 units of origin tables (see kRBlockUnits)
     uint16_t sbit[kRBits]; // swizzled tile slot of each sub-cube bit
     uint8_t perm[kTileBits - kRBits];  // thread-index bit j -> tile-local position outside the sub-cube
     uint8_t quad_mask;     // bit j: the visit starts with a plain DOT/ACC/Re record for xr = 31 ^ (1 << j) ("simple
@@ -51,7 +53,10 @@ struct TRBlock {           // 32 bytes = 2 units
     uint32_t n_groups;
 };
 static_assert(sizeof(TRBlock) == 32, "TRBlock layout");
-constexpr uint32_t kRBlockUnits = 2;
+// A sub-cube visit in the blob: TRBlock (2 units) + origin tables (6 units): uint32 lo[16], hi[8] with
+// (origin << 16 | swizzled origin) of thread t = lo[t & 15] ^ hi[t >> 4]  (the swizzle is XOR-linear and the two
+// halves deposit disjoint bits), so a thread finds its sub-cube with two broadcast-free LDS instead of ~40 ALU ops.
+constexpr uint32_t kRBlockUnits = 8;
 
 // ---- record stream (16-byte units) ----------------------------------------------------------------------------
 // DOT / DIAG record: header + 16 doubles.   w = sum_k tab[k] * prod_k  with
