@@ -196,7 +196,7 @@ def reference_gates_per_rotation(wl: dict) -> float:
 
 
 # ------------------------------------------------------------------------------------------------------------------
-def run_reference(args, n, nelec):
+def run_reference(args, n, nelec, out):
     """--impl reference: the reference's own CPU algorithm on the host cores (oracle port; qibo is not installable)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -217,7 +217,7 @@ def run_reference(args, n, nelec):
         "cpu_baseline": {**{k: last[k] for k in ("unit", "cores", "kind", "sample")}, "value": v},
         "e2e": {"value": v, "unit": unit_for(n), "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }  # fmt: skip
-    print(json.dumps(line))
+    out.emit(line)
 
 
 def config_dict(wl, args):
@@ -231,17 +231,32 @@ def config_dict(wl, args):
     }  # fmt: skip
 
 
+class JsonStdout:
+    """The driver reads ONE JSON line from stdout: everything else a library prints there (NCCL's version banner,
+    ...) is sent to stderr by pointing fd 1 at fd 2 until the line is written."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, line: dict) -> None:
+        sys.stdout.flush()
+        os.write(self.saved, (json.dumps(line) + "\n").encode())
+
+
 def main():
     args = parse_args()
     n = args.qubits if args.qubits is not None else DEFAULT_QUBITS.get(args.gpus, 30)
     nelec = args.electrons if args.electrons is not None else {30: 14}.get(n, 2 * ((n * 14 // 30) // 2))
+    out = JsonStdout()
     if args.impl == "reference":
-        run_reference(args, n, nelec)
+        run_reference(args, n, nelec, out)
         return
     if args.gpus > 1:
         from bench_sharded import main_sharded
 
-        main_sharded(args, n, nelec)
+        main_sharded(args, n, nelec, out)
         return
 
     import torch
@@ -326,7 +341,7 @@ def main():
         "wall_ms_per_step": 1e3 * wall / args.steps,
         "clocks": clock_info, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
     }  # fmt: skip
-    print(json.dumps(line))
+    out.emit(line)
 
 
 def k2_fp64_roofline(wl, prof, args):

@@ -9,7 +9,7 @@ import time
 import numpy as np
 
 
-def main_sharded(args, n: int, nelec: int) -> None:
+def main_sharded(args, n: int, nelec: int, out) -> None:
     import torch
     import torch.distributed as dist
 
@@ -99,6 +99,6 @@ def main_sharded(args, n: int, nelec: int) -> None:
                          "nvlink_GBps_per_direction_incl_barriers": nvlink, "nvlink_peak_GBps": 770.0},
             "cpu_baseline": None,
         }  # fmt: skip
-        print(json.dumps(line))
+        out.emit(line)
     ex.close()
     dist.destroy_process_group()
