@@ -43,8 +43,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         sys.stderr.write(proc.stdout + proc.stderr)
     if proc.returncode:
         raise RuntimeError("nvcc failed building libqibochem_b200.so")
-    with open(os.path.join(HERE, "csrc", "ptxas_info.txt"), "w") as f:
-        f.write(proc.stderr)
+    with open(os.path.join(HERE, "csrc", "ptxas_info.txt"), "w") as f:  # registers / spills / shared memory per kernel
+        f.write("".join(line for line in proc.stderr.splitlines(keepends=True) if "Compile time" not in line))
     return LIB
 
 
