@@ -517,3 +517,28 @@ def test_tiled_expectation_random_dense_hamiltonian(DeviceState, n, seed):
         assert abs(e - ref) < 1e-9 * max(1.0, np.abs(cs).sum() / 50)
         st.set_option("k2_mode", 1)
         assert abs(st.expectation(xs, zs, cs) - e) < 1e-9 * max(1.0, np.abs(cs).sum() / 50)
+
+
+def test_empty_and_degenerate_inputs(DeviceState):
+    """Empty programs / term lists, tile modes requested on registers too small for a tile, repeated identical calls."""
+    n = 6
+    psi = random_state(n, 4)
+    with DeviceState(n) as st:
+        st.from_numpy(psi)
+        assert st.apply_pauli_rotations([], [], []) == 0
+        assert st.expectation([], [], []) == 0.0
+        e, g = st.energy_gradient([], [], [], [3], [5], [0.5])
+        assert g.size == 0 and abs(e - O.expectation_masks(psi, [3], [5], [0.5])) < E_TOL
+        e, g = st.energy_gradient([1], [2], [0.3], [], [], [])
+        assert e == 0.0 and g.tolist() == [0.0]
+        st.set_option("k2_mode", 2)  # tiles need >= 12 local qubits: falls back to sweeps
+        st.set_option("k1_mode", 2)
+        xs, zs, cs = [0, 7, 7, 40], [5, 1, 6, 9], [0.3, -0.2, 0.9, 1.5]
+        assert abs(st.expectation(xs, zs, cs) - O.expectation_masks(psi, xs, zs, cs)) < E_TOL
+        st.apply_pauli_rotations([7, 7], [1, 6], [0.4, -0.1])
+        ref = O.apply_pauli_rotation(O.apply_pauli_rotation(psi, 7, 1, 0.4), 7, 6, -0.1)
+        assert np.abs(st.to_numpy() - ref).max() < AMP_TOL
+        with pytest.raises(RuntimeError):
+            st.set_option("no_such_option", 1)
+        with pytest.raises(RuntimeError):
+            st.expectation([1 << n], [0], [1.0])  # mask outside the register
