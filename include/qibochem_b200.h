@@ -122,6 +122,13 @@ int qc_outcome_variance(qc_state* h, const uint64_t* keys, const int64_t* counts
                         const uint64_t* zmask, const double* coeff, size_t J, double mean, double* sumsq_unweighted_out,
                         double* sumsq_weighted_out);
 
+/* ---- host-side term grouping (replaces the O(T^2) string parsing + networkx colouring of
+ *      src/qibochem/measurement/util.py:22-79 reached from _measurement_basis_rotations("qwc")) -------------------- */
+/* Greedy colouring ("largest_first", networkx's default) of the non-commutation graph of T Pauli terms given as
+ * masks; qubitwise != 0: qubit-wise commutation, else general commutation.  colour_out[k] <- group of term k. */
+int qc_group_commuting(size_t T, const uint64_t* xmask, const uint64_t* zmask, int qubitwise, int32_t* colour_out,
+                       int32_t* n_colours_out);
+
 /* ---- live profiler / launch counter (bench.py: roofline of the dominant kernel, gpu_launches) ----------------- */
 /* Kernel classes: 0 K0 init, 1 K1 rotation pass, 2 K2 expectation sweeps, 3 reductions, 4 K5 sampling, 5 K3 shot
  * statistics, 6 K4 exchange, 7 K2 tiled expectation passes, 8 gradient sweeps.  Launch counts and algorithmic bytes are always accumulated; when enabled, every

@@ -38,6 +38,7 @@ SIGNATURES = {
     "qc_parity_sums": (C.c_int, [_vp, _vp, _vp, C.c_size_t, C.c_int, _u64p, C.c_size_t, _i64p]),
     "qc_frequencies": (C.c_int, [_vp, _vp, C.c_size_t, C.c_int, C.c_uint64, _u64p, _i64p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "qc_outcome_variance": (C.c_int, [_vp, _u64p, _i64p, C.c_size_t, _u64p, _f64p, C.c_size_t, C.c_double, _f64p, _f64p]),
+    "qc_group_commuting": (C.c_int, [C.c_size_t, _u64p, _u64p, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "qc_profile_enable": (C.c_int, [_vp, C.c_int]),
     "qc_profile_reset": (C.c_int, [_vp]),
     "qc_transfer_bytes": (C.c_int, [_vp, _u64p, _u64p, C.c_int]),

@@ -49,9 +49,33 @@ def _conflict_matrix(x: np.ndarray, z: np.ndarray, qubitwise: bool, rows: slice)
     return par != 0
 
 
-def group_commuting_masks(x, z, qubitwise: bool = True, block: int = 2048) -> list[list[int]]:
+def group_commuting_masks(x, z, qubitwise: bool = True) -> list[list[int]]:
     """Greedy ("largest_first") colouring of the non-commutation graph.  Returns groups of term indices, each group
-    in ascending index order, groups ordered by colour."""
+    in ascending index order, groups ordered by colour.  Host-native (``csrc/grouping.cpp``, OpenMP): 10^5 terms take
+    seconds; ``_group_commuting_masks_numpy`` is the same algorithm in numpy (kept as the test oracle)."""
+    import ctypes as C
+
+    from qibochem_b200 import _native
+
+    x = np.ascontiguousarray(np.asarray(x, dtype=np.uint64))
+    z = np.ascontiguousarray(np.asarray(z, dtype=np.uint64))
+    if x.size == 0:
+        return []
+    colour = np.zeros(x.size, dtype=np.int32)
+    ncol = C.c_int32(0)
+    u64p = C.POINTER(C.c_uint64)
+    _native.check(
+        _native.load().qc_group_commuting(x.size, x.ctypes.data_as(u64p), z.ctypes.data_as(u64p), int(bool(qubitwise)),
+                                          colour.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(ncol)),
+        "qc_group_commuting",
+    )  # fmt: skip
+    order = np.argsort(colour, kind="stable")
+    bounds = np.searchsorted(colour[order], np.arange(ncol.value + 1))
+    return [order[bounds[c] : bounds[c + 1]].tolist() for c in range(ncol.value)]
+
+
+def _group_commuting_masks_numpy(x, z, qubitwise: bool = True, block: int = 2048) -> list[list[int]]:
+    """numpy restatement of ``group_commuting_masks`` (test oracle for the native routine)."""
     x = np.asarray(x, dtype=np.uint64)
     z = np.asarray(z, dtype=np.uint64)
     T = x.size

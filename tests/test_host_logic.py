@@ -299,3 +299,30 @@ def test_k2_tiled_plan_serves_every_xmask_once(native_lib, n, T):
     assert int(stats[8:16].sum()) == n_cubes and n_pass <= n_cubes
     if T >= 8000:
         assert n_pass * 20 < n_x and n_tiled / n_cubes > 2.5
+
+
+@pytest.mark.parametrize("qubitwise", [True, False])
+def test_native_grouping_equals_numpy_restatement(native_lib, qubitwise):
+    """qc_group_commuting (C++/OpenMP) == the numpy restatement of networkx's largest_first greedy colouring, on random
+    masks and on a molecular-structured term list; groups are valid (pairwise commuting)."""
+    from qibochem_b200 import synthetic
+    from qibochem_b200.measurement.optimization import _group_commuting_masks_numpy, group_commuting_masks
+
+    rng = np.random.default_rng(5)
+    cases = [(rng.integers(0, 2**9, size=400, dtype=np.uint64), rng.integers(0, 2**9, size=400, dtype=np.uint64))]
+    hx, hz, _, _ = synthetic.molecular_like_hamiltonian(12, 1500)
+    cases.append((hx, hz))
+    for x, z in cases:
+        got = group_commuting_masks(x, z, qubitwise)
+        assert got == _group_commuting_masks_numpy(x, z, qubitwise)
+        assert sorted(k for g in got for k in g) == list(range(x.size))
+        for g in got[:20]:
+            for a in g[:10]:
+                for b in g[:10]:
+                    xa, za, xb, zb = int(x[a]), int(z[a]), int(x[b]), int(z[b])
+                    if qubitwise:
+                        common = (xa | za) & (xb | zb)
+                        assert ((xa ^ xb) | (za ^ zb)) & common == 0
+                    else:
+                        assert bin((xa & zb) ^ (za & xb)).count("1") % 2 == 0
+    assert group_commuting_masks([], [], qubitwise) == []
