@@ -89,7 +89,31 @@ static int apply_gate1q(qc_state* h, double2* psi, int bit, const Mat2& m) {
 // ---------------------------------------------------------------------------------------------------------------
 // probabilities: per-chunk sums, prefix sums over chunks, inverse-CDF draws
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int kChunkLog2 = 12;  // 4096 amplitudes (64 KB) per chunk
+// A shot costs a binary search over the chunk prefix sums plus a scan of (on average) half a chunk, so chunks are kept
+// small: 128 amplitudes (2 KB) up to 25 qubits, growing so that the single-CTA prefix sum handles <= 2^18 chunk sums.
+constexpr int kMinChunkLog2 = 7;
+constexpr int kMaxChunksLog2 = 18;
+inline int chunk_log2_for(int n) { return std::min(n, std::max(kMinChunkLog2, n - kMaxChunksLog2)); }
+
+// small chunks (<= 1024 amplitudes): one warp per chunk, lane-strided, fixed-order warp reduction
+__global__ void __launch_bounds__(kThreads) chunk_prob_warp_kernel(const double2* __restrict__ psi, uint64_t dim,
+                                                                   int chunk_log2, double* __restrict__ chunk_sum) {
+    const uint64_t nchunks = dim >> chunk_log2;
+    const uint64_t csize = 1ull << chunk_log2;
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = ((uint64_t)blockIdx.x * kThreads + threadIdx.x) >> 5;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * kThreads) >> 5;
+    for (uint64_t c = warp; c < nchunks; c += nwarps) {
+        const double2* p = psi + (c << chunk_log2);
+        double acc = 0.0;
+        for (uint64_t k = lane; k < csize; k += 32) {
+            const double2 a = p[k];
+            acc += a.x * a.x + a.y * a.y;
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) chunk_sum[c] = acc;
+    }
+}
 
 __global__ void __launch_bounds__(kThreads) chunk_prob_kernel(const double2* __restrict__ psi, uint64_t dim,
                                                               int chunk_log2, double* __restrict__ chunk_sum) {
@@ -361,13 +385,18 @@ int qc_sample(qc_state* h, uint64_t x_basis_mask, uint64_t y_basis_mask, size_t 
         }
         src = h->scratch_psi;
     }
-    const int chunk_log2 = std::min(h->n, kChunkLog2);
+    const int chunk_log2 = chunk_log2_for(h->n);
     const uint64_t nchunks = h->dim >> chunk_log2;
     if (h->ensure_partials(nchunks)) return 1;
-    const int nb = (int)std::min<uint64_t>(nchunks, (uint64_t)h->sm_count * kCtasPerSm);
     {
         LaunchScope ls(h, kK5Sampling, 16.0 * (double)h->dim);
-        chunk_prob_kernel<<<nb, kThreads, 0, h->stream>>>(src, h->dim, chunk_log2, h->d_partials);
+        if (chunk_log2 <= 10) {
+            const int nb = (int)std::min<uint64_t>((nchunks * 32 + kThreads - 1) / kThreads, (uint64_t)h->sm_count * kCtasPerSm);
+            chunk_prob_warp_kernel<<<nb, kThreads, 0, h->stream>>>(src, h->dim, chunk_log2, h->d_partials);
+        } else {
+            const int nb = (int)std::min<uint64_t>(nchunks, (uint64_t)h->sm_count * kCtasPerSm);
+            chunk_prob_kernel<<<nb, kThreads, 0, h->stream>>>(src, h->dim, chunk_log2, h->d_partials);
+        }
     }
     QC_CHECK(cudaGetLastError());
     {
