@@ -141,6 +141,8 @@ struct TileRun {
     int8_t hb_l;          // highest set bit of xl (-1 if xl == 0)
     int8_t n_sup_l;
     int8_t ma, mb;        // a' = c a + f (-i)^ma b,   b' = c b + f (-i)^mb a
+    // per slot group k (warp-uniform part of a thread's slots): tile slot bits | pext(bits, sup_l) << 12 | parity(bits & z0_l) << 31
+    uint32_t kpack[kRotTileSize / kRotTileThreads];
 };
 struct TileBatch {
     uint64_t s_mask;
@@ -170,17 +172,25 @@ __device__ __forceinline__ double2 mul_pow_minus_i(int m, double2 v) {
     }
 }
 
-constexpr int kTileRunTable = 32;  // (cos, sin) entries per run staged in shared memory (support <= 5 bits)
+constexpr int kTileRunTable = 16;  // (cos, sin) entries per run staged in shared memory (support <= 4 bits)
 
 __global__ void __launch_bounds__(kRotTileThreads, 3)
     rot_tiled_kernel(double2* __restrict__ psi, int n, const TileBatch batch, const double2* __restrict__ table) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double2* tile = reinterpret_cast<double2*>(smem_raw);
-    double2* stab = tile + kRotTileSize;  // [n_runs][kTileRunTable]
+    double2* stab = tile + kRotTileSize;                                                      // [n_runs][kTileRunTable]
+    uint8_t* spre = reinterpret_cast<uint8_t*>(stab + kMaxBatchRuns * kTileRunTable);         // [n_runs][threads]
     for (int e = threadIdx.x; e < batch.n_runs * kTileRunTable; e += kRotTileThreads) {
         const TileRun& d = batch.run[e / kTileRunTable];
         const int k = e % kTileRunTable;
         if (k < (1 << (d.n_sup_l + __popcll(d.sup_outer)))) stab[e] = __ldg(&table[d.table_off + k]);
+    }
+    // The part of a slot's table index and sign that comes from the thread id does not depend on the tile: computed once.
+    for (int r = 0; r < batch.n_runs; ++r) {
+        const TileRun& d = batch.run[r];
+        const uint32_t t0 = d.xl ? (uint32_t)insert_zero_bit(threadIdx.x, d.hb_l) : threadIdx.x;
+        spre[r * kRotTileThreads + threadIdx.x] =
+            (uint8_t)((d.sup_l ? pext32(t0, d.sup_l) : 0u) | ((__popc(t0 & d.z0_l) & 1u) << 7));
     }
     const uint64_t n_tiles = 1ull << (n - kRotTileBits);
     // amplitude offset of tile slot t = k * 256 + tid: low 8 tile bits from tid, high 4 from k
@@ -217,34 +227,29 @@ __global__ void __launch_bounds__(kRotTileThreads, 3)
             const double2* tab = stab + r * kTileRunTable;
             uint32_t outer_idx = 0;
             if (d.sup_outer) outer_idx = gather_bits(base, d.sup_outer) << d.n_sup_l;
-            const unsigned outer_par = (unsigned)__popcll(base & d.z0_outer);
-            // A thread's slots share the part that comes from tid; the part from k is warp-uniform.
+            const uint32_t pre = spre[r * kRotTileThreads + threadIdx.x];
+            const uint32_t idx0 = outer_idx | (pre & 0x7fu);
+            const unsigned par0 = (unsigned)__popcll(base & d.z0_outer) + (pre >> 7);
             if (d.xl == 0) {
                 const uint32_t t0 = threadIdx.x;
-                const uint32_t idx0 = outer_idx | (d.sup_l ? pext32(t0, d.sup_l) : 0u);
-                const unsigned par0 = outer_par + (unsigned)__popc(t0 & d.z0_l);
 #pragma unroll
                 for (int k = 0; k < kRotTileSize / kRotTileThreads; ++k) {
-                    const uint32_t tk = (uint32_t)k * kRotTileThreads;
-                    const uint32_t t = t0 | tk;
+                    const uint32_t kp = d.kpack[k];
+                    const uint32_t t = t0 | (kp & 0xfffu);
                     const double2 a = tile[t];
-                    const double2 cs = tab[idx0 | (d.sup_l ? pext32(tk, d.sup_l) : 0u)];
-                    const unsigned par = par0 + (unsigned)__popc(tk & d.z0_l);
-                    const double ms = (par & 1u) ? cs.y : -cs.y;  // multiply by (c - i s0 s)
+                    const double2 cs = tab[idx0 | ((kp >> 12) & 0x3ffu)];
+                    const double ms = ((par0 + (kp >> 31)) & 1u) ? cs.y : -cs.y;  // multiply by (c - i s0 s)
                     tile[t] = make_double2(cs.x * a.x - ms * a.y, cs.x * a.y + ms * a.x);
                 }
             } else {
                 const uint32_t t0 = (uint32_t)insert_zero_bit(threadIdx.x, d.hb_l);
-                const uint32_t idx0 = outer_idx | (d.sup_l ? pext32(t0, d.sup_l) : 0u);
-                const unsigned par0 = outer_par + (unsigned)__popc(t0 & d.z0_l);
 #pragma unroll
                 for (int k = 0; k < kRotTileSize / 2 / kRotTileThreads; ++k) {
-                    const uint32_t tk = (uint32_t)insert_zero_bit((uint32_t)k * kRotTileThreads, d.hb_l);
-                    const uint32_t t = t0 | tk, u = t ^ d.xl;
+                    const uint32_t kp = d.kpack[k];
+                    const uint32_t t = t0 | (kp & 0xfffu), u = t ^ d.xl;
                     const double2 a = tile[t], b = tile[u];
-                    const double2 cs = tab[idx0 | (d.sup_l ? pext32(tk, d.sup_l) : 0u)];
-                    const unsigned par = par0 + (unsigned)__popc(tk & d.z0_l);
-                    const double f = (par & 1u) ? -cs.y : cs.y;
+                    const double2 cs = tab[idx0 | ((kp >> 12) & 0x3ffu)];
+                    const double f = ((par0 + (kp >> 31)) & 1u) ? -cs.y : cs.y;
                     const double2 ub = mul_pow_minus_i(d.ma, b), ua = mul_pow_minus_i(d.mb, a);
                     tile[t] = make_double2(cs.x * a.x + f * ub.x, cs.x * a.y + f * ub.y);
                     tile[u] = make_double2(cs.x * b.x + f * ua.x, cs.x * b.y + f * ua.y);
@@ -403,7 +408,7 @@ int apply_rotations_to(qc_state* h, double2* target, size_t R, const uint64_t* x
     h->h2d_bytes += total_entries * sizeof(double2);
     const double2* dtab = (const double2*)h->arena.dev;
 
-    const size_t tile_smem = (size_t)(kRotTileSize + kMaxBatchRuns * kTileRunTable) * sizeof(double2);
+    const size_t tile_smem = (size_t)(kRotTileSize + kMaxBatchRuns * kTileRunTable) * sizeof(double2) + (size_t)kMaxBatchRuns * kRotTileThreads;
     for (const Batch& bt : batches) {
         LaunchScope ls(h, kK1Rotation, 32.0 * (double)h->dim);  // every amplitude read + written once per pass
         if (bt.S) {
@@ -440,6 +445,16 @@ int apply_rotations_to(qc_state* h, double2* target, size_t R, const uint64_t* x
                 tr.n_sup_l = (int8_t)__builtin_popcount(tr.sup_l);
                 tr.ma = (int8_t)((((ny0 + 1) % 4) + 4) % 4);
                 tr.mb = (int8_t)((((1 - ny0) % 4) + 4) % 4);
+                const int n_k = tr.xl ? kRotTileSize / 2 / kRotTileThreads : kRotTileSize / kRotTileThreads;
+                for (int kk = 0; kk < n_k; ++kk) {
+                    uint32_t tk = (uint32_t)kk * kRotTileThreads;
+                    if (tr.xl) tk = ((tk >> tr.hb_l) << (tr.hb_l + 1)) | (tk & ((1u << tr.hb_l) - 1u));  // insert a 0 at hb_l
+                    uint32_t ext = 0;
+                    int pos = 0;
+                    for (uint32_t m = tr.sup_l; m; m &= m - 1, ++pos)
+                        if ((tk >> __builtin_ctz(m)) & 1u) ext |= 1u << pos;
+                    tr.kpack[kk] = tk | (ext << 12) | ((uint32_t)(__builtin_popcount(tk & tr.z0_l) & 1) << 31);
+                }
             }
             QC_CHECK(cudaFuncSetAttribute(rot_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem));
             const uint64_t n_tiles = 1ull << (h->n - kRotTileBits);
