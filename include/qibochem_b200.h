@@ -55,8 +55,8 @@ int qc_set_basis_state(qc_state* h, uint64_t index, int has_one);
 /* ---- K1: Pauli rotations  (replaces the 16-40 gate passes per _expi_pauli, _ansatz.py:80-92, executed by
  *      qibo's backend gate loop reached from Circuit.__call__) ---------------------------------------------- */
 /* Applies R rotations IN ORDER.  Consecutive strings that share an x-mask and commute are fused into one pass
- * (the 8 strings of a JW double excitation always do), and consecutive runs whose x-masks fit one 12-bit
- * shared-memory tile are applied in ONE in-place pass.  n_passes_out (may be NULL) receives the number of full-state
+ * (the 8 strings of a JW double excitation always do), and consecutive runs whose x-masks are linearly independent
+ * (up to 5 distinct masks, e.g. 5 double excitations = 40 strings) are applied in ONE in-place pass.  n_passes_out (may be NULL) receives the number of full-state
  * passes actually launched. */
 int qc_apply_pauli_rotations(qc_state* h, size_t R, const uint64_t* xmask, const uint64_t* zmask,
                              const double* angle, int* n_passes_out);
@@ -70,8 +70,9 @@ int qc_expectation(qc_state* h, size_t T, const uint64_t* xmask, const uint64_t*
                    double* energy_out, double* per_term, int* n_sweeps_out);
 /* Options: "k2_mode" = 0 auto (default), 1 one HBM sweep per x-mask, 2 shared-memory tiles serving many x-masks per
  * HBM read (needs >= 12 local qubits; falls back to sweeps for x-masks that do not fit a tile).
- * "k1_mode" = 0 auto (default: consecutive fused runs whose x-masks fit a 12-bit tile share one in-place HBM pass),
- * 1 one HBM pass per fused run, 2 tiles even for a lone run. */
+ * "k1_mode" = 0 auto (default: consecutive fused runs with linearly independent x-masks -- up to 5 distinct ones --
+ * are applied from registers in one in-place HBM pass), 1 one HBM pass per fused run, 2 shared-memory tiles
+ * (consecutive runs whose x-masks fit a 12-bit tile), 3 register phases even for a lone run. */
 int qc_set_option(qc_state* h, const char* key, int64_t value);
 /* Host-only (no GPU needed): plans the tiled expectation of a term list and reports its shape.  stats_out: 16 x
  * uint64 {x-masks, tiled x-masks, HBM passes, register sub-cubes, DOT records, LIN entries, leftover terms (sweep

@@ -16,6 +16,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <functional>
 
 #include "common.cuh"
 
@@ -268,6 +269,137 @@ __global__ void __launch_bounds__(kRotTileThreads, 3)
     }
 }
 
+// ---- K1O: a PHASE of consecutive fused runs applied from registers in one in-place HBM pass ------------------------
+// The x-masks of a phase are linearly independent over GF(2) (at most 5 distinct ones, each possibly used by several
+// runs, plus diagonal runs).  They generate a group of 2^d index translations; a thread loads the 32 amplitudes of
+// 2^(5-d) orbits of that group (element e = (orbit << d) | E lives at  c ^ XOR_{i in E} x_i,  c = the orbit's
+// representative: the thread's global number deposited into the index bits that are not pivots of the x-masks),
+// applies EVERY run of the phase to them -- run i pairs element E with E ^ (1 << basis(i)), a compile-time butterfly
+// -- and stores them back: one read and one write of the shard per phase, no shared-memory traffic.  Loads and stores
+// stay coalesced because consecutive lanes own consecutive representatives and an x-mask only permutes a 32-lane
+// block.  UCCSD streams give 5 excitations (40 strings) per pass.
+constexpr int kOrbitBits = 5;
+constexpr int kOrbitSize = 1 << kOrbitBits;
+constexpr int kOrbitThreads = 128;
+constexpr int kMaxPhaseRuns = 16;
+constexpr int kPhaseTable = 16;  // (cos, sin) entries per run staged in shared memory (support <= 4 bits)
+
+struct PhaseRun {
+    uint64_t x;          // pairing mask (0 => diagonal run)
+    uint64_t z0;         // z-mask of the run's first string
+    uint64_t sup_mask;   // union support of z_k ^ z_0, pair bit removed (table index = its bits of the canonical element)
+    uint32_t table_off;  // first table entry (double2 units)
+    int8_t hb;           // highest set bit of x (-1 if x == 0)
+    int8_t basis;        // which basis vector x is (-1 for a diagonal run)
+    int8_t ma;           // a' = c a + f (-i)^ma b,  b' = c b + f (-i)^(2-ma) a   for the pair (a = hb clear, b)
+    uint8_t xidx;        // pext(x, sup_mask): table-index change when the canonical element is the partner
+    // Index / sign / orientation are XOR-linear in the element's index c ^ elem[e]; the elem[e] parts are per run:
+    uint32_t epar;       // bit e: parity(elem[e] & z0)
+    uint32_t ehb;        // bit e: bit hb of elem[e]
+    uint8_t xpar;        // parity(x & z0)
+    uint8_t pad[3];
+    uint8_t eidx[32];    // pext(elem[e], sup_mask)
+};
+struct PhaseDesc {
+    uint64_t elem[kOrbitSize];  // index offset of register element e relative to the thread's first representative
+    uint8_t pivot[kOrbitBits];  // pivot bit of each basis vector, ascending
+    int n_pivots;
+    int n_runs;
+    PhaseRun run[kMaxPhaseRuns];
+};
+
+// (gr + i gi) * v
+__device__ __forceinline__ double2 cmul2(double gr, double gi, double2 v) {
+    return make_double2(gr * v.x - gi * v.y, gr * v.y + gi * v.x);
+}
+
+// Run on basis vector I: element e (bit I clear) pairs with e | 1 << I.  ODD = ma is odd (w = -+i), else w = +-1.
+// c_hb / c_idx / c_par: orientation bit, table index and sign parity of the thread's representative c (per run).
+template <int I, bool ODD>
+__device__ __forceinline__ void orbit_butterfly(double2 (&a)[kOrbitSize], const PhaseRun& d, const double2* __restrict__ tab,
+                                                uint32_t c_hb, uint32_t c_idx, uint32_t c_par, double wsign) {
+#pragma unroll
+    for (int e = 0; e < kOrbitSize; ++e) {
+        if (e & (1 << I)) continue;
+        const int e1 = e | (1 << I);
+        const uint32_t sw = c_hb ^ ((d.ehb >> e) & 1u);  // 1: a[e] is the partner (highest x bit set), a[e1] canonical
+        const uint32_t idx = c_idx ^ d.eidx[e] ^ (sw ? d.xidx : 0u);
+        const uint32_t par = c_par ^ ((d.epar >> e) & 1u) ^ (sw & d.xpar);
+        const double2 cs = tab[idx];
+        const double f = par ? -cs.y : cs.y;
+        const double2 u0 = a[e], u1 = a[e1];
+        if (!ODD) {
+            // w = wsign (+-1): canonical a' = c a + f w b, b' = c b - f w a; roles swap with sw
+            const double g = sw ? -f * wsign : f * wsign;
+            a[e] = make_double2(fma(g, u1.x, cs.x * u0.x), fma(g, u1.y, cs.x * u0.y));
+            a[e1] = make_double2(fma(-g, u0.x, cs.x * u1.x), fma(-g, u0.y, cs.x * u1.y));
+        } else {
+            // w = i wsign: a' = c a + i g b and b' = c b + i g a (the same g for both, whatever the orientation)
+            const double g = f * wsign;
+            a[e] = make_double2(fma(-g, u1.y, cs.x * u0.x), fma(g, u1.x, cs.x * u0.y));
+            a[e1] = make_double2(fma(-g, u0.y, cs.x * u1.x), fma(g, u0.x, cs.x * u1.y));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kOrbitThreads, 2)
+    rot_orbit_kernel(double2* __restrict__ psi, uint64_t n_threads_total, const PhaseDesc ph, const double2* __restrict__ table) {
+    __shared__ double2 stab[kMaxPhaseRuns * kPhaseTable];
+    for (int e = threadIdx.x; e < ph.n_runs * kPhaseTable; e += kOrbitThreads) {
+        const PhaseRun& d = ph.run[e / kPhaseTable];
+        const int k = e % kPhaseTable;
+        if (k < (1 << __popcll(d.sup_mask))) stab[e] = __ldg(&table[d.table_off + k]);
+    }
+    __syncthreads();
+    for (uint64_t tg = (uint64_t)blockIdx.x * kOrbitThreads + threadIdx.x; tg < n_threads_total;
+         tg += (uint64_t)gridDim.x * kOrbitThreads) {
+        uint64_t c0 = tg;  // first representative: the thread number deposited into the non-pivot index bits
+        for (int j = 0; j < ph.n_pivots; ++j) c0 = insert_zero_bit(c0, ph.pivot[j]);
+        double2 a[kOrbitSize];
+#pragma unroll
+        for (int e = 0; e < kOrbitSize; ++e) a[e] = psi[c0 ^ ph.elem[e]];
+        for (int r = 0; r < ph.n_runs; ++r) {
+            const PhaseRun& d = ph.run[r];
+            const double2* tab = stab + r * kPhaseTable;
+            if (d.basis < 0) {
+#pragma unroll
+                for (int e = 0; e < kOrbitSize; ++e) {
+                    const uint64_t s = c0 ^ ph.elem[e];
+                    const double2 cs = tab[d.sup_mask ? gather_bits(s, d.sup_mask) : 0u];
+                    const double ms = (__popcll(s & d.z0) & 1) ? cs.y : -cs.y;  // multiply by (c - i s0 s)
+                    const double2 v = a[e];
+                    a[e] = make_double2(cs.x * v.x - ms * v.y, cs.x * v.y + ms * v.x);
+                }
+                continue;
+            }
+            // w = (-i)^ma: +1, -i, -1, +i
+            const double wsign = (d.ma == 0 || d.ma == 3) ? 1.0 : -1.0;
+            const uint32_t c_hb = (uint32_t)(c0 >> d.hb) & 1u;
+            const uint32_t c_idx = d.sup_mask ? gather_bits(c0, d.sup_mask) : 0u;
+            const uint32_t c_par = (uint32_t)__popcll(c0 & d.z0) & 1u;
+#define QC_BFLY(I)                                                                  \
+    case I:                                                                         \
+        if (d.ma & 1)                                                               \
+            orbit_butterfly<I, true>(a, d, tab, c_hb, c_idx, c_par, wsign);         \
+        else                                                                        \
+            orbit_butterfly<I, false>(a, d, tab, c_hb, c_idx, c_par, wsign);        \
+        break;
+            switch (d.basis) {
+                QC_BFLY(0) QC_BFLY(1) QC_BFLY(2) QC_BFLY(3)
+                default:
+                    if (d.ma & 1)
+                        orbit_butterfly<4, true>(a, d, tab, c_hb, c_idx, c_par, wsign);
+                    else
+                        orbit_butterfly<4, false>(a, d, tab, c_hb, c_idx, c_par, wsign);
+                    break;
+            }
+#undef QC_BFLY
+        }
+#pragma unroll
+        for (int e = 0; e < kOrbitSize; ++e) psi[c0 ^ ph.elem[e]] = a[e];
+    }
+}
+
 static inline void pow_minus_i(int m, double& re, double& im) {
     switch (((m % 4) + 4) % 4) {
         case 0: re = 1.0; im = 0.0; break;
@@ -326,14 +458,62 @@ int apply_rotations_to(qc_state* h, double2* target, size_t R, const uint64_t* x
     std::vector<Run> runs;
     plan_runs(R, xmask, zmask, runs);
 
-    // ---- batches: consecutive runs whose x-masks fit, with index bits 0..2, into one 12-bit tile
+    // ---- batches.  k1_mode 0 (auto) / 3: register-blocked PHASES (K1O): consecutive runs whose distinct x-masks are
+    // linearly independent (<= 5 of them); 2: shared-memory TILES (K1T): consecutive runs whose x-masks fit, with index
+    // bits 0..2, into one 12-bit tile; 1: one sweep per fused run.
     struct Batch {
         size_t first, count;
-        uint64_t S;  // 0 => single run, one of the sweep kernels
+        uint64_t S;  // tile bits of a K1T batch (0 otherwise)
+        int phase;   // index into `phases` for a K1O batch (-1 otherwise)
+    };
+    struct Phase {
+        std::vector<uint64_t> basis;  // distinct x-masks in order of first use
+        std::vector<uint64_t> red;    // the same span in reduced row echelon form (pivot = highest set bit)
     };
     std::vector<Batch> batches;
-    {
-        const bool tiles_ok = h->n >= kRotTileBits && k1_mode != 1;
+    std::vector<Phase> phases;
+    const bool orbit_ok = h->n >= 10 && (k1_mode == 0 || k1_mode == 3);
+    if (orbit_ok) {
+        auto small = [&](const Run& g) { return (1 << __builtin_popcountll(g.sup)) <= kPhaseTable; };
+        auto reduce = [](const std::vector<uint64_t>& red, uint64_t v) {
+            for (uint64_t r : red)
+                if ((v >> (63 - __builtin_clzll(r))) & 1ull) v ^= r;
+            return v;
+        };
+        size_t i = 0;
+        while (i < runs.size()) {
+            if (!small(runs[i])) {
+                batches.push_back({i, 1, 0ull, -1});
+                ++i;
+                continue;
+            }
+            Phase ph;
+            size_t j = i;
+            while (j < runs.size() && j - i < (size_t)kMaxPhaseRuns && small(runs[j])) {
+                const uint64_t x = runs[j].x;
+                if (x != 0 && std::find(ph.basis.begin(), ph.basis.end(), x) == ph.basis.end()) {
+                    const uint64_t v = reduce(ph.red, x);
+                    if (v == 0 || ph.basis.size() == (size_t)kOrbitBits) break;  // dependent on the span / orbit is full
+                    const int pv = 63 - __builtin_clzll(v);
+                    for (uint64_t& r : ph.red)
+                        if ((r >> pv) & 1ull) r ^= v;  // keep the echelon form fully reduced: pivot columns are unit columns
+                    ph.red.push_back(v);
+                    std::sort(ph.red.begin(), ph.red.end(), std::greater<uint64_t>());
+                    ph.basis.push_back(x);
+                }
+                ++j;
+            }
+            if (j - i >= 2 || k1_mode == 3) {
+                batches.push_back({i, j - i, 0ull, (int)phases.size()});
+                phases.push_back(ph);
+            } else {
+                batches.push_back({i, 1, 0ull, -1});
+                j = i + 1;
+            }
+            i = j;
+        }
+    } else {
+        const bool tiles_ok = h->n >= kRotTileBits && k1_mode == 2;
         const uint64_t low = 7ull;
         size_t i = 0;
         while (i < runs.size()) {
@@ -346,15 +526,13 @@ int apply_rotations_to(qc_state* h, double2* target, size_t R, const uint64_t* x
                     U |= runs[j].x;
                     ++j;
                 }
-                if (j - i >= 2 || k1_mode == 2) {
-                    uint64_t S = U | low;
-                    for (int b = 0; __builtin_popcountll(S) < kRotTileBits; ++b) S |= 1ull << b;
-                    batches.push_back({i, j - i, S});
-                    i = j;
-                    continue;
-                }
+                uint64_t S = U | low;
+                for (int b = 0; __builtin_popcountll(S) < kRotTileBits; ++b) S |= 1ull << b;
+                batches.push_back({i, j - i, S, -1});
+                i = j;
+                continue;
             }
-            batches.push_back({i, 1, 0ull});
+            batches.push_back({i, 1, 0ull, -1});
             i += 1;
         }
     }
@@ -411,6 +589,62 @@ int apply_rotations_to(qc_state* h, double2* target, size_t R, const uint64_t* x
     const size_t tile_smem = (size_t)(kRotTileSize + kMaxBatchRuns * kTileRunTable) * sizeof(double2) + (size_t)kMaxBatchRuns * kRotTileThreads;
     for (const Batch& bt : batches) {
         LaunchScope ls(h, kK1Rotation, 32.0 * (double)h->dim);  // every amplitude read + written once per pass
+        if (bt.phase >= 0) {
+            const Phase& phs = phases[bt.phase];
+            PhaseDesc pd;
+            memset(&pd, 0, sizeof(pd));
+            const int d = (int)phs.basis.size();
+            std::vector<int> piv;
+            for (uint64_t r : phs.red) piv.push_back(63 - __builtin_clzll(r));
+            std::sort(piv.begin(), piv.end());
+            pd.n_pivots = d;
+            for (int j = 0; j < d; ++j) pd.pivot[j] = (uint8_t)piv[j];
+            auto deposit = [&](uint64_t v) {  // insert zeros at the pivot positions (ascending)
+                for (int pv : piv) v = ((v >> pv) << (pv + 1)) | (v & ((1ull << pv) - 1ull));
+                return v;
+            };
+            for (int e = 0; e < kOrbitSize; ++e) {
+                const uint64_t o = (uint64_t)e >> d;
+                uint64_t off = deposit(o << (h->n - kOrbitBits));
+                for (int b = 0; b < d; ++b)
+                    if ((e >> b) & 1) off ^= phs.basis[b];
+                pd.elem[e] = off;
+            }
+            pd.n_runs = (int)bt.count;
+            for (size_t k = 0; k < bt.count; ++k) {
+                const Run& g = runs[bt.first + k];
+                PhaseRun& pr = pd.run[k];
+                const int ny0 = __builtin_popcountll(g.x & g.z0);
+                pr.x = g.x;
+                pr.z0 = g.z0;
+                pr.sup_mask = g.sup;
+                pr.table_off = table_off[bt.first + k];
+                pr.hb = (int8_t)g.hb;
+                pr.basis = -1;
+                for (int b = 0; b < d; ++b)
+                    if (phs.basis[b] == g.x) pr.basis = (int8_t)b;
+                pr.ma = (int8_t)((((ny0 + 1) % 4) + 4) % 4);
+                auto pext = [&](uint64_t v) {
+                    uint32_t out = 0;
+                    int pos = 0;
+                    for (uint64_t m = g.sup; m; m &= m - 1, ++pos)
+                        if ((v >> __builtin_ctzll(m)) & 1ull) out |= 1u << pos;
+                    return out;
+                };
+                pr.xidx = (uint8_t)pext(g.x);
+                pr.xpar = (uint8_t)(__builtin_popcountll(g.x & g.z0) & 1);
+                for (int e = 0; e < kOrbitSize; ++e) {
+                    pr.eidx[e] = (uint8_t)pext(pd.elem[e]);
+                    pr.epar |= (uint32_t)(__builtin_popcountll(pd.elem[e] & g.z0) & 1) << e;
+                    if (g.hb >= 0) pr.ehb |= (uint32_t)((pd.elem[e] >> g.hb) & 1ull) << e;
+                }
+            }
+            const uint64_t n_threads = h->dim >> kOrbitBits;
+            const int nb = (int)std::min<uint64_t>((n_threads + kOrbitThreads - 1) / kOrbitThreads, (uint64_t)h->sm_count * 16);
+            h->h2d_bytes += sizeof(PhaseDesc);  // kernel parameters
+            rot_orbit_kernel<<<nb, kOrbitThreads, 0, h->stream>>>(target, n_threads, pd, dtab);
+            continue;
+        }
         if (bt.S) {
             TileBatch tb;
             memset(&tb, 0, sizeof(tb));

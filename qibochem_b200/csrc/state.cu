@@ -229,7 +229,7 @@ int qc_set_option(qc_state* h, const char* key, int64_t value) {
         return 0;
     }
     if (strcmp(key, "k1_mode") == 0) {
-        QC_REQUIRE(value >= 0 && value <= 2, "qc_set_option: k1_mode must be 0 (auto), 1 (one pass per run) or 2 (tiles)");
+        QC_REQUIRE(value >= 0 && value <= 3, "qc_set_option: k1_mode must be 0 (auto), 1 (one pass per run), 2 (tiles) or 3 (register phases)");
         h->k1_mode = (int)value;
         return 0;
     }

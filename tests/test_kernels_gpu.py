@@ -358,13 +358,13 @@ def test_tiled_rotation_batches_match_oracle(DeviceState, n):
         ref = O.apply_pauli_rotation(ref, x, z, p)
     with DeviceState(n) as st:
         results = {}
-        for mode in (1, 0, 2):
+        for mode in (1, 0, 2, 3):
             st.set_option("k1_mode", mode)
             st.from_numpy(psi)
             passes = st.apply_pauli_rotations(xs, zs, phis)
             results[mode] = (passes, st.to_numpy())
             assert np.abs(results[mode][1] - ref).max() < AMP_TOL, f"k1_mode={mode}"
-        assert results[0][0] < results[1][0]  # batching saved passes
+        assert results[0][0] < results[1][0] and results[2][0] < results[1][0]  # batching saved passes
 
 
 def test_tiled_rotations_on_uccsd_stream(DeviceState):
@@ -380,12 +380,12 @@ def test_tiled_rotations_on_uccsd_stream(DeviceState):
         OC.pauli_rotation(ref, n, x, z, a)
     with DeviceState(n) as st:
         out = {}
-        for mode in (1, 0):
+        for mode in (1, 0, 2):
             st.set_option("k1_mode", mode)
             st.set_basis_state(synthetic.hf_index(n, ne))
             out[mode] = (st.apply_pauli_rotations(rx, rz, ra), st.to_numpy())
             assert np.abs(out[mode][1] - ref).max() < AMP_TOL
-        assert out[1][0] == n_exc and out[0][0] * 2 < n_exc
+        assert out[1][0] == n_exc and out[0][0] * 2 < n_exc and out[2][0] * 2 < n_exc
 
 
 def test_full_size_30q_properties(DeviceState):
@@ -532,7 +532,7 @@ def test_empty_and_degenerate_inputs(DeviceState):
         e, g = st.energy_gradient([1], [2], [0.3], [], [], [])
         assert e == 0.0 and g.tolist() == [0.0]
         st.set_option("k2_mode", 2)  # tiles need >= 12 local qubits: falls back to sweeps
-        st.set_option("k1_mode", 2)
+        st.set_option("k1_mode", 3)
         xs, zs, cs = [0, 7, 7, 40], [5, 1, 6, 9], [0.3, -0.2, 0.9, 1.5]
         assert abs(st.expectation(xs, zs, cs) - O.expectation_masks(psi, xs, zs, cs)) < E_TOL
         st.apply_pauli_rotations([7, 7], [1, 6], [0.4, -0.1])
@@ -542,3 +542,35 @@ def test_empty_and_degenerate_inputs(DeviceState):
             st.set_option("no_such_option", 1)
         with pytest.raises(RuntimeError):
             st.expectation([1 << n], [0], [1.0])  # mask outside the register
+
+
+@pytest.mark.parametrize("n", [10, 11, 14])
+def test_register_phase_rotations_edge_cases(DeviceState, n):
+    """K1O phases: repeated x-masks, x-masks in the span of earlier ones (phase break), more than five distinct masks,
+    low / high / diagonal runs mixed, z-masks with bits everywhere; register phases == one pass per run == oracle."""
+    rng = np.random.default_rng(77 + n)
+    psi = random_state(n, 3 * n + 1)
+    b = [1 << int(k) for k in rng.permutation(n)[:7]]
+    xmasks = [b[0] | b[1], b[2] | b[3], b[0] | b[1], 0, b[0] | b[1] | b[2] | b[3],  # the last one is x0 ^ x1: dependent
+              b[4], b[5], b[6], b[4] | b[5] | b[6], b[0], 1, 3, 2, 0, (1 << (n - 1)) | 1, b[2] | b[3]]  # fmt: skip
+    xs, zs, phis = [], [], []
+    for x in xmasks:
+        z0 = int(rng.integers(0, 2**n))
+        members = [z0]
+        for _ in range(12):
+            dz = int(rng.integers(0, 2**n)) & (x | 0x5)
+            if bin(x & dz).count("1") % 2 == 0 and (z0 ^ dz) not in members:
+                members.append(z0 ^ dz)
+            if len(members) == 3:
+                break
+        for z in members:
+            xs.append(x), zs.append(z), phis.append(float(rng.uniform(-1.5, 1.5)))
+    ref = psi.copy()
+    for x, z, p in zip(xs, zs, phis):
+        ref = O.apply_pauli_rotation(ref, x, z, p)
+    with DeviceState(n) as st:
+        for mode in (3, 0, 1):
+            st.set_option("k1_mode", mode)
+            st.from_numpy(psi)
+            st.apply_pauli_rotations(xs, zs, phis)
+            assert np.abs(st.to_numpy() - ref).max() < AMP_TOL, f"k1_mode={mode}"
