@@ -292,13 +292,11 @@ struct PhaseRun {
     int8_t hb;           // highest set bit of x (-1 if x == 0)
     int8_t basis;        // which basis vector x is (-1 for a diagonal run)
     int8_t ma;           // a' = c a + f (-i)^ma b,  b' = c b + f (-i)^(2-ma) a   for the pair (a = hb clear, b)
-    uint8_t xidx;        // pext(x, sup_mask): table-index change when the canonical element is the partner
-    // Index / sign / orientation are XOR-linear in the element's index c ^ elem[e]; the elem[e] parts are per run:
-    uint32_t epar;       // bit e: parity(elem[e] & z0)
-    uint32_t ehb;        // bit e: bit hb of elem[e]
-    uint8_t xpar;        // parity(x & z0)
-    uint8_t pad[3];
-    uint8_t eidx[32];    // pext(elem[e], sup_mask)
+    int8_t pad;
+    // Index / sign / orientation of a pair are XOR-linear in the element's index c ^ elem[e].  The parts that do not
+    // depend on the thread are tabulated per run for both values h of the representative's orientation bit
+    // (bit hb of c):  sel[h][e] = table-index part (bits 0..3) | sign-parity part (bit 4) | swap flag (bit 5)
+    uint8_t sel[2][32];
 };
 struct PhaseDesc {
     uint64_t elem[kOrbitSize];  // index offset of register element e relative to the thread's first representative
@@ -322,11 +320,10 @@ __device__ __forceinline__ void orbit_butterfly(double2 (&a)[kOrbitSize], const 
     for (int e = 0; e < kOrbitSize; ++e) {
         if (e & (1 << I)) continue;
         const int e1 = e | (1 << I);
-        const uint32_t sw = c_hb ^ ((d.ehb >> e) & 1u);  // 1: a[e] is the partner (highest x bit set), a[e1] canonical
-        const uint32_t idx = c_idx ^ d.eidx[e] ^ (sw ? d.xidx : 0u);
-        const uint32_t par = c_par ^ ((d.epar >> e) & 1u) ^ (sw & d.xpar);
-        const double2 cs = tab[idx];
-        const double f = par ? -cs.y : cs.y;
+        const uint32_t v = c_hb ? d.sel[1][e] : d.sel[0][e];  // two warp-uniform bytes, picked per thread
+        const uint32_t sw = v & 32u;                         // a[e] is the partner (highest x bit set), a[e1] canonical
+        const double2 cs = tab[c_idx ^ (v & 15u)];
+        const double f = ((c_par ^ (v >> 4)) & 1u) ? -cs.y : cs.y;
         const double2 u0 = a[e], u1 = a[e1];
         if (!ODD) {
             // w = wsign (+-1): canonical a' = c a + f w b, b' = c b - f w a; roles swap with sw
@@ -631,12 +628,15 @@ int apply_rotations_to(qc_state* h, double2* target, size_t R, const uint64_t* x
                         if ((v >> __builtin_ctzll(m)) & 1ull) out |= 1u << pos;
                     return out;
                 };
-                pr.xidx = (uint8_t)pext(g.x);
-                pr.xpar = (uint8_t)(__builtin_popcountll(g.x & g.z0) & 1);
+                const uint32_t xidx = pext(g.x), xpar = (uint32_t)(__builtin_popcountll(g.x & g.z0) & 1);
                 for (int e = 0; e < kOrbitSize; ++e) {
-                    pr.eidx[e] = (uint8_t)pext(pd.elem[e]);
-                    pr.epar |= (uint32_t)(__builtin_popcountll(pd.elem[e] & g.z0) & 1) << e;
-                    if (g.hb >= 0) pr.ehb |= (uint32_t)((pd.elem[e] >> g.hb) & 1ull) << e;
+                    const uint32_t eidx = pext(pd.elem[e]);
+                    const uint32_t epar = (uint32_t)(__builtin_popcountll(pd.elem[e] & g.z0) & 1);
+                    const uint32_t ehb = g.hb >= 0 ? (uint32_t)((pd.elem[e] >> g.hb) & 1ull) : 0u;
+                    for (uint32_t hbit = 0; hbit < 2; ++hbit) {
+                        const uint32_t sw = hbit ^ ehb;  // element e has the highest x bit set: the canonical one is e ^ x
+                        pr.sel[hbit][e] = (uint8_t)((eidx ^ (sw ? xidx : 0u)) | ((epar ^ (sw & xpar)) << 4) | (sw << 5));
+                    }
                 }
             }
             const uint64_t n_threads = h->dim >> kOrbitBits;
