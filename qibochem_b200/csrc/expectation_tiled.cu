@@ -178,8 +178,8 @@ __global__ void __launch_bounds__(kTileThreads, 2)
         __syncthreads();
 
         for (uint32_t rb = 0; rb < pass.n_rblocks; ++rb) {
-            const uint4 b0 = blob[rb * kRBlockUnits];      // sbit[0..4], perm[0..5]
-            const uint4 b1 = blob[rb * kRBlockUnits + 1];  // perm[6], pad, rec_off, n_recs, n_groups
+            const uint4 b0 = blob[rb * kRBlockUnits];      // sbit[0..4], quad_mask
+            const uint4 b1 = blob[rb * kRBlockUnits + 1];  // rec_off, n_recs, n_groups
             // tile-local origin of this thread's sub-cube (and its swizzled slot) from the visit's two origin tables
             const uint32_t* otab = reinterpret_cast<const uint32_t*>(blob + rb * kRBlockUnits + 2);
             const uint32_t packed = otab[threadIdx.x & 15u] ^ otab[16u + (threadIdx.x >> 4)];
@@ -196,24 +196,28 @@ __global__ void __launch_bounds__(kTileThreads, 2)
                 if (p & 16) off ^= sb4;
                 a[p] = tile[off];
             }
-            const uint4* rp = blob + b1.y;
-            // ---- simple quads of this cube (x = cube minus bit j): straight-line code, no per-record dispatch
-            const uint32_t quad_mask = (b1.x >> 8) & 31u;
-#define QC_QUAD(J)                                                                                   \
-    if (quad_mask & (1u << J)) {                                                                     \
-        const uint4 hd = *rp;                                                                        \
-        const double w = dot_pairs<31 ^ (1 << J), false>(a, reinterpret_cast<const double2*>(rp + 1)); \
-        if (J & 1)                                                                                   \
-            acc1 += apply_sign(w, sign_parity(base, org, hd));                                       \
-        else                                                                                         \
-            acc0 += apply_sign(w, sign_parity(base, org, hd));                                       \
-        rp += kDotUnits;                                                                             \
+            const uint4* rp = blob + b1.x;
+            const uint32_t rho8 = ((threadIdx.x >> 6) & 1u) * 8u;  // two-table records: units to skip for rho = 1
+            // ---- simple quads of this cube (coordinate vectors of weight 4 and 3): straight-line code, no dispatch
+            const uint32_t quad_mask = b0.z >> 16;
+#define QC_QUAD(S, XR)                                                                                  \
+    if (quad_mask & (1u << S)) {                                                                        \
+        const uint4 hd = *rp;                                                                           \
+        const uint32_t two = (hd.w >> 12) & 1u;                                                         \
+        const double w = dot_pairs<XR, false>(a, reinterpret_cast<const double2*>(rp + 1 + two * rho8)); \
+        if (S & 1)                                                                                      \
+            acc1 += apply_sign(w, sign_parity(base, org, hd));                                          \
+        else                                                                                            \
+            acc0 += apply_sign(w, sign_parity(base, org, hd));                                          \
+        rp += kDotUnits + two * 8u;                                                                     \
     }
-            QC_QUAD(0) QC_QUAD(1) QC_QUAD(2) QC_QUAD(3) QC_QUAD(4)
+            QC_QUAD(0, 30) QC_QUAD(1, 29) QC_QUAD(2, 27) QC_QUAD(3, 23) QC_QUAD(4, 15)
+            QC_QUAD(5, 7) QC_QUAD(6, 11) QC_QUAD(7, 13) QC_QUAD(8, 14) QC_QUAD(9, 19)
+            QC_QUAD(10, 21) QC_QUAD(11, 22) QC_QUAD(12, 25) QC_QUAD(13, 26) QC_QUAD(14, 28)
 #undef QC_QUAD
             // ---- generic records
             double A0 = 0.0, A1 = 0.0, A2 = 0.0, A3 = 0.0;
-            for (uint32_t r = 0; GENERIC && r < b1.z; ++r) {
+            for (uint32_t r = 0; GENERIC && r < b1.y; ++r) {
                 const uint4 hd = *rp;
                 const uint32_t meta = hd.w;
                 const uint32_t kind = meta_kind(meta);
@@ -239,8 +243,9 @@ __global__ void __launch_bounds__(kTileThreads, 2)
 #pragma unroll
                 for (int p = 0; p < 32; ++p) asm volatile("" : "+d"(a[p].x), "+d"(a[p].y));
                 const uint32_t sel = kind == kRecDot ? (meta & 63u) : (kind == kRecDiagHi ? 32u : 0u);
-                const double w = dot_dispatch(sel, a, reinterpret_cast<const double2*>(rp + 1));
-                rp += kDotUnits;
+                const uint32_t two = (meta >> 12) & 1u;
+                const double w = dot_dispatch(sel, a, reinterpret_cast<const double2*>(rp + 1 + two * rho8));
+                rp += kDotUnits + two * 8u;
                 const uint32_t mode = meta_mode(meta);
                 if (mode == kModeAcc) {
                     acc0 += apply_sign(w, sign_parity(base, org, hd));

@@ -34,7 +34,8 @@ struct XG {  // terms of one x-mask
 
 struct Term {  // one term seen from inside a sub-cube
     uint64_t z_not_r;
-    uint32_t pk;  // z on the sub-cube bits (pair groups: highest x bit cleared)
+    uint32_t pk;  // sign pattern over the cube's elements (pair groups: highest x coordinate cleared); bit 5: z on the
+                  // parity cube's sixth bit (the sign then also depends on the representative's sixth bit rho)
     int odd;
     double d;
 };
@@ -96,10 +97,19 @@ struct GroupRecs {
 };
 constexpr size_t kLinChunk = 200;  // LIN entries per record
 
+// rglob: index-bit positions of the cube's five COORDINATE bits (bit i of an element index E is read there);
+// gglob: the five generators as index-bit masks; r_global: the union of the coordinate bits.
+// rho_pos: index-bit position of a parity cube's sixth bit (-1 for a unit cube).
 GroupRecs emit_group(const XG& g, const uint64_t* zs, const double* cs, uint64_t S, const int* spos, uint64_t r_global,
-                     const int* rglob /*global positions of the R bits*/, PlanStats& st) {
+                     const int* rglob, const uint64_t* gglob, int rho_pos, PlanStats& st) {
+    const uint64_t rho_bit = rho_pos >= 0 ? (1ull << rho_pos) : 0ull;
     GroupRecs out;
-    const uint32_t xr = compress_bits(g.x, rglob, kRBits);
+    const uint32_t xr = compress_bits(g.x, rglob, kRBits);  // coordinate vector of x (x is in the generators' span)
+    auto zeta = [&](uint64_t z) {  // sign of element E under z: (-1)^{popc(E & zeta)}  (beyond the representative's part)
+        uint32_t out_bits = 0;
+        for (int j = 0; j < kRBits; ++j) out_bits |= (uint32_t)(popc64(gglob[j] & z) & 1) << j;
+        return out_bits;
+    };
     const uint32_t hbbit = xr ? (1u << (31 - __builtin_clz(xr))) : 0u;
     const double pair_scale = xr ? 2.0 : 1.0;
     const int halves = xr ? 1 : 2;
@@ -110,8 +120,8 @@ GroupRecs emit_group(const XG& g, const uint64_t* zs, const double* cs, uint64_t
         const uint64_t z = zs[t];
         const int ny = popc64(g.x & z);
         Term tm;
-        tm.z_not_r = z & ~r_global;
-        tm.pk = compress_bits(z, rglob, kRBits) & ~hbbit;
+        tm.z_not_r = z & ~(r_global | rho_bit);
+        tm.pk = (zeta(z) & ~hbbit) | ((z & rho_bit) ? 32u : 0u);
         tm.odd = ny & 1;
         tm.d = cs[t] * (((ny >> 1) & 1) ? -1.0 : 1.0);
         subs[{tm.z_not_r, tm.odd}].push_back(tm);
@@ -161,6 +171,13 @@ GroupRecs emit_group(const XG& g, const uint64_t* zs, const double* cs, uint64_t
         h.meta = meta;
         return h;
     };
+    // DOT / DIAG record: one table, or two (rho = 0, 1) when tab1 is given
+    auto push_dot = [&](std::vector<Unit16>& units, TRecHdr h, const double* tab0, const double* tab1) {
+        if (tab1) h.meta |= kMetaTwoTables;
+        push_units(units, &h, sizeof(h));
+        push_units(units, tab0, 16 * sizeof(double));
+        if (tab1) push_units(units, tab1, 16 * sizeof(double));
+    };
     // ---- pattern sums A[slot]
     if (!lin_subs.empty()) {
         for (size_t j = 0; j < by_freq.size(); ++j) {
@@ -168,11 +185,12 @@ GroupRecs emit_group(const XG& g, const uint64_t* zs, const double* cs, uint64_t
             const uint32_t pk = by_freq[j].second.first;
             const int odd = by_freq[j].second.second;
             for (int half = 0; half < halves; ++half) {
-                DotRec r;
                 const uint32_t kind = xr ? kRecDot : (half ? kRecDiagHi : kRecDiagLo);
-                r.h = header(0, rec_meta(xr, (uint32_t)odd, kind, half ? kModeAdd : kModeSet, (uint32_t)j, 0));
-                pattern_table(xr, pk, half, pair_scale, r.tab);
-                push_units(out.setup, &r, sizeof(r));
+                const TRecHdr h = header(0, rec_meta(xr, (uint32_t)odd, kind, half ? kModeAdd : kModeSet, (uint32_t)j, 0));
+                double t0[16], t1[16];
+                pattern_table(xr, pk & 31u, half, pair_scale, t0);
+                for (int k = 0; k < 16; ++k) t1[k] = -t0[k];  // a pattern with z on the sixth bit flips with rho
+                push_dot(out.setup, h, t0, (pk & 32u) ? t1 : nullptr);
                 ++out.setup_recs;
             }
         }
@@ -199,48 +217,70 @@ GroupRecs emit_group(const XG& g, const uint64_t* zs, const double* cs, uint64_t
     // ---- subgroups with their own weight table
     for (size_t i = 0; i < tab_subs.size(); ++i) {
         Atom atom;
+        bool any0 = false, any1 = false;
+        for (const Term& tm : *tab_subs[i]) ((tm.pk & 32u) ? any1 : any0) = true;
         for (int half = 0; half < halves; ++half) {
-            DotRec r;
             const uint32_t kind = xr ? kRecDot : (half ? kRecDiagHi : kRecDiagLo);
-            r.h = header(tab_keys[i].first, rec_meta(xr, (uint32_t)tab_keys[i].second, kind, kModeAcc, 0, 0));
-            for (int k = 0; k < 16; ++k) r.tab[k] = 0.0;
-            double pat[16];
+            // every term has z on the sixth bit: one table, the representative's sixth bit joins the thread's sign
+            const uint64_t key = tab_keys[i].first | ((any1 && !any0) ? rho_bit : 0ull);
+            const TRecHdr h = header(key, rec_meta(xr, (uint32_t)tab_keys[i].second, kind, kModeAcc, 0, 0));
+            double t0[16], t1[16], pat[16];
+            for (int k = 0; k < 16; ++k) t0[k] = t1[k] = 0.0;
             for (const Term& tm : *tab_subs[i]) {
-                pattern_table(xr, tm.pk, half, pair_scale * tm.d, pat);
-                for (int k = 0; k < 16; ++k) r.tab[k] += pat[k];
+                pattern_table(xr, tm.pk & 31u, half, pair_scale * tm.d, pat);
+                const double s1 = ((tm.pk & 32u) && any0) ? -1.0 : 1.0;  // mixed record: rho = 1 flips these terms
+                for (int k = 0; k < 16; ++k) t0[k] += pat[k], t1[k] += s1 * pat[k];
             }
-            push_units(atom.units, &r, sizeof(r));
+            push_dot(atom.units, h, t0, (any0 && any1) ? t1 : nullptr);
             ++atom.n_recs;
         }
         out.atoms.push_back(std::move(atom));
     }
-    if (popc32(xr) == 4 && out.atoms.size() == 1 && out.atoms[0].n_recs == 1 && !out.atoms[0].needs_setup &&
-        tab_keys.size() == 1 && tab_keys[0].second == 0)
-        out.atoms[0].quad_slot = __builtin_ctz(31u ^ xr);
+    if (out.atoms.size() == 1 && out.atoms[0].n_recs == 1 && !out.atoms[0].needs_setup && tab_keys.size() == 1 &&
+        tab_keys[0].second == 0)
+        for (int sl = 0; sl < kQuadSlots; ++sl)
+            if (kQuadKappa[sl] == xr) out.atoms[0].quad_slot = sl;
     return out;
 }
 
-// All kRBits-subsets of the kTileBits tile-local positions.  `conflict_free` marks those that leave, outside the
-// sub-cube, positions of all three residues mod 3: only then can the lanes of a quarter warp be mapped to distinct
-// shared-memory bank groups (the others still work, with 2-way conflicts on the gather, and are used as a last resort).
+// Sub-cube candidates inside a tile (tile-local positions).  `conflict_free`: the positions the thread id is mapped
+// to (everything outside the coordinate bits) cover all three residues mod 3 -- only then can the lanes of a quarter
+// warp be mapped to distinct shared-memory bank groups (the others still work, with 2-way conflicts on the gather, and
+// are used as a last resort).
+struct Cube {
+    uint32_t span_mask;            // tile bits the cube's x-masks may touch (6 for a parity cube, 5 for a unit cube)
+    uint32_t gens[kRBits];         // generators, tile-local masks
+    int coord[kRBits];             // coordinate bit of each generator (its lowest bit), ascending
+    int rest[kTileBits - kRBits];  // tile positions the 7 thread-id bits are deposited at
+    bool conflict_free;
+};
 struct CubeCands {
-    std::vector<uint32_t> mask;
-    std::vector<char> conflict_free;
+    std::vector<Cube> parity, unit;
 };
 const CubeCands& cube_candidates() {
     static CubeCands cc;
-    if (cc.mask.empty()) {
+    if (cc.parity.empty()) {
         for (uint32_t m = 0; m < (1u << kTileBits); ++m) {
-            if (popc32(m) != kRBits) continue;
-            bool ok = true;
-            for (int res = 0; res < 3; ++res) {
-                bool any = false;
-                for (int b = res; b < kTileBits; b += 3)
-                    if (!((m >> b) & 1u)) any = true;
-                ok = ok && any;
+            const int w = popc32(m);
+            if (w != kRBits && w != kRBits + 1) continue;
+            Cube c;
+            c.span_mask = m;
+            int pos[kRBits + 1], np = 0;
+            for (int b = 0; b < kTileBits; ++b)
+                if ((m >> b) & 1u) pos[np++] = b;
+            for (int j = 0; j < kRBits; ++j) {
+                c.coord[j] = pos[j];
+                c.gens[j] = (1u << pos[j]) | (w == kRBits + 1 ? (1u << pos[kRBits]) : 0u);
             }
-            cc.mask.push_back(m);
-            cc.conflict_free.push_back(ok ? 1 : 0);
+            int nr = 0;
+            for (int b = 0; b < kTileBits; ++b)
+                if (!((m >> b) & 1u)) c.rest[nr++] = b;
+            if (w == kRBits + 1) c.rest[nr++] = pos[kRBits];  // the sixth bit: set by the thread id, flipped by odd elements
+            bool res[3] = {false, false, false};
+            for (int j = 0; j < nr; ++j)
+                if (!(w == kRBits + 1 && c.rest[j] == pos[kRBits])) res[c.rest[j] % 3] = true;  // lanes never map to the sixth bit
+            c.conflict_free = res[0] && res[1] && res[2];
+            (w == kRBits ? cc.unit : cc.parity).push_back(c);
         }
     }
     return cc;
@@ -293,7 +333,6 @@ HostPlan* build_host_plan(int n, size_t T, const uint64_t* xs, const uint64_t* z
     st.n_tiled_groups = uncovered.size() + (diag_group >= 0 ? 1 : 0);
 
     const CubeCands& cube_cands = cube_candidates();
-    const std::vector<uint32_t>& cands = cube_cands.mask;
     const int free_slots = kTileBits - 1;
     bool diag_pending = diag_group >= 0;
     int tau = std::max(1, tau0);
@@ -336,43 +375,50 @@ HostPlan* build_host_plan(int n, size_t T, const uint64_t* xs, const uint64_t* z
         std::vector<uint32_t> mine, others;
         for (uint32_t g : uncovered) ((xg[g].x & ~S) == 0 ? mine : others).push_back(g);
 
-        // ---- sub-cubes: greedy cover of this pass's x-masks by 5-bit subsets of the tile bits
+        // ---- sub-cubes: greedy cover of this pass's x-masks -- parity cubes (six tile bits) for the even-weight
+        // x-masks, unit cubes (five tile bits) for the odd-weight ones
         std::vector<uint32_t> xl(mine.size());
         for (size_t i = 0; i < mine.size(); ++i) xl[i] = compress_bits(xg[mine[i]].x, spos, kTileBits);
-        std::vector<float> cnt(cands.size(), 0.0f);
-        for (size_t i = 0; i < mine.size(); ++i)
-            for (size_t c = 0; c < cands.size(); ++c)
-                if ((xl[i] & ~cands[c]) == 0) cnt[c] += xg[mine[i]].weight;
         std::vector<char> assigned(mine.size(), 0);
-        std::vector<std::pair<uint32_t, std::vector<uint32_t>>> cubes;  // (R tile-local, group ids)
+        std::vector<std::pair<const Cube*, std::vector<uint32_t>>> cubes;  // (cube, group ids)
         float total_w = 0.0f;
-        for (;;) {
-            // lower the bar when this pass would otherwise be too thin
-            size_t best_c = 0;
-            float best = -1.0f;
-            for (size_t c = 0; c < cands.size(); ++c) {
-                const float v = cube_cands.conflict_free[c] ? cnt[c] : 0.5f * cnt[c];
-                if (v > best) best = v, best_c = c;
+        for (int round = 0; round < 2; ++round) {
+            const std::vector<Cube>& cands = round == 0 ? cube_cands.parity : cube_cands.unit;
+            auto eligible = [&](size_t i) { return !assigned[i] && ((popc32(xl[i]) & 1) == round); };
+            std::vector<float> cnt(cands.size(), 0.0f);
+            for (size_t i = 0; i < mine.size(); ++i)
+                if (eligible(i))
+                    for (size_t c = 0; c < cands.size(); ++c)
+                        if ((xl[i] & ~cands[c].span_mask) == 0) cnt[c] += xg[mine[i]].weight;
+            for (;;) {
+                size_t best_c = 0;
+                float best = -1.0f;
+                for (size_t c = 0; c < cands.size(); ++c) {
+                    const float v = cands[c].conflict_free ? cnt[c] : 0.5f * cnt[c];
+                    if (v > best) best = v, best_c = c;
+                }
+                if (best <= 0.0f) break;
+                best = cnt[best_c];
+                // lower the bar when this pass would otherwise be too thin
+                const int bar = round == 0 ? tau : 1;
+                if (best < (float)bar) {
+                    if (total_w >= (float)min_gain || tau == 1) break;
+                    --tau;
+                    continue;
+                }
+                const Cube& cube = cands[best_c];
+                std::vector<uint32_t> members;
+                for (size_t i = 0; i < mine.size(); ++i) {
+                    if (!eligible(i) || (xl[i] & ~cube.span_mask) != 0) continue;
+                    members.push_back(mine[i]);
+                    total_w += xg[mine[i]].weight;
+                    for (size_t c = 0; c < cands.size(); ++c)
+                        if ((xl[i] & ~cands[c].span_mask) == 0) cnt[c] -= xg[mine[i]].weight;
+                    assigned[i] = 1;
+                }
+                cnt[best_c] = 0.0f;
+                cubes.push_back({&cube, members});
             }
-            if (best <= 0.0f) break;
-            best = cnt[best_c];
-            if (best < (float)tau) {
-                if (total_w >= (float)min_gain || tau == 1) break;
-                --tau;
-                continue;
-            }
-            const uint32_t R = cands[best_c];
-            std::vector<uint32_t> members;
-            for (size_t i = 0; i < mine.size(); ++i) {
-                if (assigned[i] || (xl[i] & ~R) != 0) continue;
-                assigned[i] = 1;
-                members.push_back(mine[i]);
-                total_w += xg[mine[i]].weight;
-                for (size_t c = 0; c < cands.size(); ++c)
-                    if ((xl[i] & ~cands[c]) == 0) cnt[c] -= xg[mine[i]].weight;
-            }
-            cnt[best_c] = 0.0f;
-            cubes.push_back({R, members});
         }
         for (size_t i = 0; i < mine.size(); ++i)
             if (!assigned[i]) others.push_back(mine[i]);
@@ -391,7 +437,7 @@ HostPlan* build_host_plan(int n, size_t T, const uint64_t* xs, const uint64_t* z
         }
         uncovered.swap(others);
         if (diag_pending) {
-            if (cubes.empty()) cubes.push_back({cands[0], {}});
+            if (cubes.empty()) cubes.push_back({&cube_cands.parity[0], {}});
             cubes[0].second.push_back((uint32_t)diag_group);
             diag_pending = false;
         }
@@ -399,7 +445,8 @@ HostPlan* build_host_plan(int n, size_t T, const uint64_t* xs, const uint64_t* z
         // ---- emit the pass (split into several passes over the same S when its blob would exceed the cap)
         struct RB {
             TRBlock hdr;
-            std::vector<Unit16> quads[kRBits];  // simple-quad records by slot
+            int perm[kTileBits - kRBits];  // thread-id bit j -> tile position
+            std::vector<Unit16> quads[kQuadSlots];  // simple-quad records by slot
             std::vector<Unit16> recs;           // generic records
         };
         std::vector<RB> cur;       // sub-cube visits of the pass being assembled
@@ -419,20 +466,20 @@ HostPlan* build_host_plan(int n, size_t T, const uint64_t* xs, const uint64_t* z
                 pass.n_generic += rb.hdr.n_recs;
                 rb.hdr.rec_off = rec_off;
                 rec_off += (uint32_t)rb.recs.size();
-                for (int j = 0; j < kRBits; ++j) rec_off += (uint32_t)rb.quads[j].size();
+                for (int j = 0; j < kQuadSlots; ++j) rec_off += (uint32_t)rb.quads[j].size();
                 push_units(plan->units, &rb.hdr, sizeof(TRBlock));
                 uint32_t origin[24];  // lo[16] from thread bits 0..3, hi[8] from thread bits 4..6
                 for (uint32_t t = 0; t < 24; ++t) {
                     const uint32_t bits = t < 16 ? t : (t - 16) << 4;
                     uint32_t org = 0;
                     for (int j = 0; j < kTileBits - kRBits; ++j)
-                        if ((bits >> j) & 1u) org |= 1u << rb.hdr.perm[j];
+                        if ((bits >> j) & 1u) org |= 1u << rb.perm[j];
                     origin[t] = (org << 16) | k2_swizzle(org);
                 }
                 push_units(plan->units, origin, sizeof(origin));
             }
             for (RB& rb : cur) {
-                for (int j = 0; j < kRBits; ++j)
+                for (int j = 0; j < kQuadSlots; ++j)
                     plan->units.insert(plan->units.end(), rb.quads[j].begin(), rb.quads[j].end());
                 plan->units.insert(plan->units.end(), rb.recs.begin(), rb.recs.end());
             }
@@ -443,27 +490,31 @@ HostPlan* build_host_plan(int n, size_t T, const uint64_t* xs, const uint64_t* z
             cur_units = 0, cur_groups = 0;
         };
         for (auto& cube : cubes) {
-            const uint32_t R = cube.first;
-            int rpos[kRBits], rglob[kRBits];
-            {
-                uint32_t m = R;
-                for (int j = 0; j < kRBits; ++j) {
-                    rpos[j] = __builtin_ctz(m);
-                    rglob[j] = spos[rpos[j]];
-                    m &= m - 1;
-                }
+            const Cube& cb = *cube.first;
+            int rglob[kRBits];
+            uint64_t gglob[kRBits], r_global = 0;
+            for (int j = 0; j < kRBits; ++j) {
+                rglob[j] = spos[cb.coord[j]];
+                r_global |= 1ull << rglob[j];
+                gglob[j] = 0;
+                for (int b = 0; b < kTileBits; ++b)
+                    if ((cb.gens[j] >> b) & 1u) gglob[j] |= 1ull << spos[b];
             }
-            uint64_t r_global = 0;
-            for (int j = 0; j < kRBits; ++j) r_global |= 1ull << rglob[j];
+            const bool parity_cube = popc32(cb.span_mask) == kRBits + 1;
+            const int rho_local = parity_cube ? 31 - __builtin_clz(cb.span_mask) : -1;  // the sixth (highest) cube bit
+            const int rho_pos = parity_cube ? spos[rho_local] : -1;
             TRBlock blk;
             memset(&blk, 0, sizeof(blk));
-            for (int j = 0; j < kRBits; ++j) blk.sbit[j] = (uint16_t)k2_swizzle(1u << rpos[j]);
-            // thread bit -> tile position outside the cube; the three lowest thread bits get positions with distinct
-            // residues mod 3 (distinct swizzle columns => conflict-free 128-bit shared loads inside a quarter warp)
+            for (int j = 0; j < kRBits; ++j) blk.sbit[j] = (uint16_t)k2_swizzle(cb.gens[j]);
+            // thread bit -> tile position; the three lowest thread bits get positions with distinct residues mod 3
+            // (distinct swizzle columns => conflict-free 128-bit shared loads inside a quarter warp)
+            int perm_arr[kTileBits - kRBits];
             {
+                // a parity cube's sixth bit goes to thread-id bit 6 (warp-uniform: it selects the table of a two-table record)
                 std::vector<int> rest_pos, perm;
-                for (int b = 0; b < kTileBits; ++b)
-                    if (!((R >> b) & 1u)) rest_pos.push_back(b);
+                for (int j = 0; j < kTileBits - kRBits; ++j)
+                    if (cb.rest[j] != rho_local) rest_pos.push_back(cb.rest[j]);
+                std::sort(rest_pos.begin(), rest_pos.end());
                 std::vector<char> used(rest_pos.size(), 0);
                 for (int res = 0; res < 3; ++res)
                     for (size_t i = 0; i < rest_pos.size(); ++i)
@@ -474,7 +525,8 @@ HostPlan* build_host_plan(int n, size_t T, const uint64_t* xs, const uint64_t* z
                         }
                 for (size_t i = 0; i < rest_pos.size(); ++i)
                     if (!used[i]) perm.push_back(rest_pos[i]);
-                for (size_t j = 0; j < perm.size(); ++j) blk.perm[j] = (uint8_t)perm[j];
+                if (parity_cube) perm.push_back(rho_local);
+                for (size_t j = 0; j < perm.size(); ++j) perm_arr[j] = perm[j];
             }
             // groups sorted by their in-cube mask: consecutive records then take the same branch of the kernel
             std::vector<uint32_t> members = cube.second;
@@ -486,6 +538,7 @@ HostPlan* build_host_plan(int n, size_t T, const uint64_t* xs, const uint64_t* z
             auto open_visit = [&]() {
                 cur.push_back(RB());
                 cur.back().hdr = blk;
+                memcpy(cur.back().perm, perm_arr, sizeof(perm_arr));
                 cur_units += kRBlockUnits;
                 open = true;
                 visit_groups = 0;
@@ -495,7 +548,7 @@ HostPlan* build_host_plan(int n, size_t T, const uint64_t* xs, const uint64_t* z
                 open = false;
             };
             for (uint32_t g : members) {
-                GroupRecs gr = emit_group(xg[g], zs, cs, S, spos, r_global, rglob, st);
+                GroupRecs gr = emit_group(xg[g], zs, cs, S, spos, r_global, rglob, gglob, rho_pos, st);
                 bool setup_here = false, counted = false;
                 for (Atom& atom : gr.atoms) {
                     const bool want_setup = atom.needs_setup && !setup_here;
@@ -517,7 +570,7 @@ HostPlan* build_host_plan(int n, size_t T, const uint64_t* xs, const uint64_t* z
                     }
                     if (atom.quad_slot >= 0 && !((rb.hdr.quad_mask >> atom.quad_slot) & 1u)) {
                         rb.quads[atom.quad_slot] = atom.units;
-                        rb.hdr.quad_mask |= (uint8_t)(1u << atom.quad_slot);
+                        rb.hdr.quad_mask |= (uint16_t)(1u << atom.quad_slot);
                     } else {
                         rb.recs.insert(rb.recs.end(), atom.units.begin(), atom.units.end());
                         rb.hdr.n_recs += atom.n_recs;
@@ -540,18 +593,35 @@ HostPlan* build_host_plan(int n, size_t T, const uint64_t* xs, const uint64_t* z
 
 double check_host_plan(const HostPlan* plan, size_t T, const uint64_t* xs, const uint64_t* zs, const double* cs,
                        size_t samples, uint64_t seed) {
+    // inverse of the (XOR-linear, bijective) swizzle
+    std::vector<uint16_t> unswz(kTileSize);
+    for (uint32_t t = 0; t < (uint32_t)kTileSize; ++t) unswz[k2_swizzle(t)] = (uint16_t)t;
+    struct CubeGeom {
+        uint64_t gen[kRBits];   // generators as index-bit masks
+        int coord[kRBits];      // coordinate bit (index position) of each generator = its lowest bit
+        int spos[kTileBits];
+    };
+    auto geometry = [&](const TPass& pass, const TRBlock& blk, CubeGeom& cg) {
+        for (int j = 0; j < kTileBits; ++j) cg.spos[j] = pass.spos[j];
+        uint64_t coords = 0;
+        for (int j = 0; j < kRBits; ++j) {
+            if (blk.sbit[j] >= kTileSize) return false;
+            const uint32_t local = unswz[blk.sbit[j]];
+            if (local == 0) return false;
+            cg.gen[j] = 0;
+            for (int b = 0; b < kTileBits; ++b)
+                if ((local >> b) & 1u) cg.gen[j] |= 1ull << pass.spos[b];
+            cg.coord[j] = __builtin_ctzll(cg.gen[j]);
+            coords |= 1ull << cg.coord[j];
+        }
+        // every generator must carry exactly its own coordinate bit (so that E is read off the coordinate bits)
+        for (int j = 0; j < kRBits; ++j)
+            if ((cg.gen[j] & coords) != (1ull << cg.coord[j])) return false;
+        return popc64(coords) == kRBits;
+    };
     // index: x-mask -> record segments (pass, sub-cube visit, first unit, unit count), in execution order
     struct Where {
         uint32_t pass, rblock_unit, first, units;
-    };
-    auto cube_bits = [](const TPass& pass, const TRBlock& blk, int* rglob) {
-        for (int j = 0; j < kRBits; ++j) {
-            rglob[j] = -1;
-            for (int b = 0; b < kTileBits; ++b)
-                if (k2_swizzle(1u << b) == blk.sbit[j]) rglob[j] = pass.spos[b];
-            if (rglob[j] < 0) return false;
-        }
-        return true;
     };
     std::unordered_map<uint64_t, std::vector<Where>> where;
     for (uint32_t p = 0; p < plan->passes.size(); ++p) {
@@ -561,36 +631,47 @@ double check_host_plan(const HostPlan* plan, size_t T, const uint64_t* xs, const
             TRBlock blk;
             const uint32_t hdr_unit = pass.blob_off + rb * kRBlockUnits;
             memcpy(&blk, &plan->units[hdr_unit], sizeof(blk));
-            int rglob[kRBits];
-            if (!cube_bits(pass, blk, rglob)) return -1.0;
-            // the thread -> origin map must be a bijection onto the tile positions outside the cube
-            uint32_t seen = 0;
-            for (int j = 0; j < kTileBits - kRBits; ++j) seen |= 1u << blk.perm[j];
-            for (int j = 0; j < kRBits; ++j)
-                for (int b = 0; b < kTileBits; ++b)
-                    if (k2_swizzle(1u << b) == blk.sbit[j]) seen |= 1u << b;
-            if (seen != (1u << kTileBits) - 1u) return -1.0;
+            CubeGeom cg;
+            if (!geometry(pass, blk, cg)) return -1.0;
+            // the 128 thread representatives x 32 elements must tile the 4096 slots exactly once
+            uint32_t origin[24];
+            memcpy(origin, &plan->units[hdr_unit + 2], sizeof(origin));
+            std::vector<char> seen(kTileSize, 0);
+            uint32_t lgen[kRBits];
+            for (int j = 0; j < kRBits; ++j) lgen[j] = unswz[blk.sbit[j]];
+            for (uint32_t t = 0; t < (uint32_t)kTileThreads; ++t) {
+                const uint32_t packed = origin[t & 15u] ^ origin[16u + (t >> 4)];
+                const uint32_t org = packed >> 16;
+                if (k2_swizzle(org) != (packed & 0xffffu)) return -1.0;
+                for (uint32_t e = 0; e < 32; ++e) {
+                    uint32_t slot = org;
+                    for (int j = 0; j < kRBits; ++j)
+                        if ((e >> j) & 1u) slot ^= lgen[j];
+                    if (seen[slot]) return -1.0;
+                    seen[slot] = 1;
+                }
+            }
             uint32_t u = pass.blob_off + blk.rec_off;
             const uint32_t n_quads = (uint32_t)popc32(blk.quad_mask);
-            {   // the quad records must be plain DOT/ACC/Re records of the announced masks, in ascending slot order
+            {   // the quad records must be plain DOT/ACC/Re records of the announced coordinate vectors, in slot order
                 uint32_t uq = u;
-                for (int j = 0; j < kRBits; ++j) {
-                    if (!((blk.quad_mask >> j) & 1u)) continue;
+                for (int sl = 0; sl < kQuadSlots; ++sl) {
+                    if (!((blk.quad_mask >> sl) & 1u)) continue;
                     TRecHdr h;
                     memcpy(&h, &plan->units[uq], sizeof(h));
                     if (meta_kind(h.meta) != kRecDot || meta_mode(h.meta) != kModeAcc || meta_im(h.meta) != 0 ||
-                        meta_xr(h.meta) != (31u ^ (1u << j)))
+                        meta_xr(h.meta) != kQuadKappa[sl])
                         return -1.0;
-                    uq += kDotUnits;
+                    uq += dot_units(h.meta);
                 }
             }
             for (uint32_t r = 0; r < n_quads + blk.n_recs; ++r) {
                 TRecHdr h;
                 memcpy(&h, &plan->units[u], sizeof(h));
-                const uint32_t units = meta_kind(h.meta) == kRecLin ? 1 + kLinEntryUnits * meta_count(h.meta) : kDotUnits;
+                const uint32_t units = meta_kind(h.meta) == kRecLin ? 1 + kLinEntryUnits * meta_count(h.meta) : dot_units(h.meta);
                 uint64_t x = 0;
                 for (int j = 0; j < kRBits; ++j)
-                    if ((meta_xr(h.meta) >> j) & 1u) x |= 1ull << rglob[j];
+                    if ((meta_xr(h.meta) >> j) & 1u) x ^= cg.gen[j];
                 auto& v = where[x];
                 if (!v.empty() && v.back().rblock_unit == hdr_unit && v.back().first + v.back().units == u)
                     v.back().units += units;
@@ -632,16 +713,22 @@ double check_host_plan(const HostPlan* plan, size_t T, const uint64_t* xs, const
             const TPass& pass = plan->passes[w.pass];
             TRBlock blk;
             memcpy(&blk, &plan->units[w.rblock_unit], sizeof(blk));
-            int rglob[kRBits], spos[kTileBits];
-            cube_bits(pass, blk, rglob);
-            for (int j = 0; j < kTileBits; ++j) spos[j] = pass.spos[j];
-            const uint32_t xr = compress_bits(x, rglob, kRBits);
+            CubeGeom cg;
+            geometry(pass, blk, cg);
+            // coordinate vector of x: read at the coordinate bits (x is in the span, checked when `where` was built)
+            uint32_t xr = 0;
+            for (int j = 0; j < kRBits; ++j) xr |= (uint32_t)((x >> cg.coord[j]) & 1ull) << j;
             uint64_t i = i_raw;
-            int k = -1;  // index of p among the products of a record
+            auto elem_of = [&](uint64_t idx) {
+                uint32_t e = 0;
+                for (int j = 0; j < kRBits; ++j) e |= (uint32_t)((idx >> cg.coord[j]) & 1ull) << j;
+                return e;
+            };
+            int k = -1;  // index of the element among the products of a record
             if (xr) {
                 const int hb = 31 - __builtin_clz(xr);
-                if ((i >> rglob[hb]) & 1ull) i ^= x;  // canonical element of the pair in THIS sub-cube
-                const uint32_t p = compress_bits(i, rglob, kRBits);
+                if ((elem_of(i) >> hb) & 1u) i ^= x;  // canonical element of the pair in THIS sub-cube
+                const uint32_t p = elem_of(i);
                 int kk = 0;
                 for (int q = 0; q < 32; ++q) {
                     if ((q >> hb) & 1) continue;
@@ -652,8 +739,11 @@ double check_host_plan(const HostPlan* plan, size_t T, const uint64_t* xs, const
             // every segment must weight the SAME pair: W is invariant under i -> i^x up to the sign (-1)^{nY}, which
             // only matters for odd-nY (Im) terms; compare per segment against the direct weight at its own i
             if (first_seg) i_ref = i;
-            const uint32_t p = compress_bits(i, rglob, kRBits);
-            const uint32_t org_local = compress_bits(i, spos, kTileBits);
+            const uint32_t p = elem_of(i);
+            uint64_t c = i;  // the thread's representative: element 0 of the orbit of i
+            for (int j = 0; j < kRBits; ++j)
+                if ((p >> j) & 1u) c ^= cg.gen[j];
+            const uint32_t org_local = compress_bits(c, cg.spos, kTileBits);
             const double flip_im = (i == i_ref) ? 1.0 : -1.0;  // Im q changes sign under i <-> i^x
             double A[kSlots] = {0, 0, 0, 0};
             int a_type[kSlots] = {0, 0, 0, 0};
@@ -666,7 +756,7 @@ double check_host_plan(const HostPlan* plan, size_t T, const uint64_t* xs, const
                     for (uint32_t e = 0; e < meta_count(h.meta); ++e) {
                         LinEntry le;
                         memcpy(&le, &plan->units[u + 1 + kLinEntryUnits * e], sizeof(le));
-                        const int par = (popc64(i & le.z_outer) + popc32(org_local & le.z_rest)) & 1;
+                        const int par = (popc64(c & le.z_outer) + popc32(org_local & le.z_rest)) & 1;
                         for (int j = 0; j < kSlots; ++j)
                             got[a_type[j]] += (par ? -1.0 : 1.0) * le.c[j] * A[j] * (a_type[j] ? flip_im : 1.0);
                     }
@@ -674,8 +764,14 @@ double check_host_plan(const HostPlan* plan, size_t T, const uint64_t* xs, const
                     continue;
                 }
                 DotRec r;
-                memcpy(&r, &plan->units[u], sizeof(r));
-                u += kDotUnits;
+                memcpy(&r.h, &plan->units[u], sizeof(r.h));
+                {
+                    // thread-id bit 6 of a parity cube = the representative's sixth bit (highest bit of the generators)
+                    const int rho_pos = popc64(cg.gen[0]) == 2 ? 63 - __builtin_clzll(cg.gen[0]) : -1;
+                    const uint32_t rho = (rho_pos >= 0 && (h.meta & kMetaTwoTables)) ? (uint32_t)((c >> rho_pos) & 1ull) : 0u;
+                    memcpy(r.tab, &plan->units[u + 1 + 8 * rho], sizeof(r.tab));
+                }
+                u += dot_units(h.meta);
                 double wgt;
                 if (kind == kRecDot) {
                     wgt = r.tab[k];
@@ -685,7 +781,7 @@ double check_host_plan(const HostPlan* plan, size_t T, const uint64_t* xs, const
                 }
                 const uint32_t mode = meta_mode(h.meta);
                 if (mode == kModeAcc) {
-                    const int par = (popc64(i & h.z_outer) + popc32(org_local & h.z_rest)) & 1;
+                    const int par = (popc64(c & h.z_outer) + popc32(org_local & h.z_rest)) & 1;
                     got[meta_im(h.meta)] += (par ? -wgt : wgt) * (meta_im(h.meta) ? flip_im : 1.0);
                 } else {
                     const uint32_t sl = meta_slot(h.meta);

@@ -41,21 +41,31 @@ struct TPass {             // kernel parameter (constant bank)
     uint32_t pad;
 };
 
+// A sub-cube visit.  The 32 amplitudes a thread holds are  c ^ XOR_{i in E} gen_i  (E = 0..31) for five GENERATORS
+// gen_i (tile-local masks, linearly independent) and the thread's representative c:
+//   * parity cube: gen_i = {q_i, q_5} for six tile bits q_0..q_5 -- the span is every EVEN-weight subset of the six
+//     bits, so one gather serves up to 15 four-bit and 15 two-bit x-masks (molecular Hamiltonians only have even ones);
+//   * unit cube:   gen_i = {r_i} for five tile bits (x-masks of odd weight).
+// An x-mask in the span has the 5-bit coordinate vector xr (which generators it is the XOR of); the pairs of a record
+// are the elements E and E ^ xr.
 struct TRBlock {           // 32 bytes = 2 units, followed by 6 units of origin tables (see kRBlockUnits)
-    uint16_t sbit[kRBits]; // swizzled tile slot of each sub-cube bit
-    uint8_t perm[kTileBits - kRBits];  // thread-index bit j -> tile-local position outside the sub-cube
-    uint8_t quad_mask;     // bit j: the visit starts with a plain DOT/ACC/Re record for xr = 31 ^ (1 << j) ("simple
-                           // quad": the 4-bit x-mask that leaves out cube bit j), in ascending j -- the kernel runs
-                           // these from straight-line code without the per-record dispatch
-    uint8_t pad[2];
+    uint16_t sbit[kRBits]; // swizzled tile slot offset of each generator (the swizzle is XOR-linear)
+    uint16_t quad_mask;    // bit s: the visit starts with a plain DOT/ACC/Re record for xr = kQuadKappa[s] ("simple
+                           // quad"), in ascending s -- the kernel runs these from straight-line code without dispatch
+    uint32_t pad;
     uint32_t rec_off;      // first record (quad records first), in units from the start of the blob
     uint32_t n_recs;       // generic records following the popcount(quad_mask) quad records
     uint32_t n_groups;
+    uint32_t pad2;
 };
 static_assert(sizeof(TRBlock) == 32, "TRBlock layout");
+// coordinate vectors with a straight-line path in the kernel: the weight-4 and weight-3 ones (in a parity cube these
+// are exactly the 15 four-bit x-masks: weight 3 means the sixth bit takes part)
+constexpr int kQuadSlots = 15;
+constexpr uint32_t kQuadKappa[kQuadSlots] = {30, 29, 27, 23, 15, 7, 11, 13, 14, 19, 21, 22, 25, 26, 28};
 // A sub-cube visit in the blob: TRBlock (2 units) + origin tables (6 units): uint32 lo[16], hi[8] with
 // (origin << 16 | swizzled origin) of thread t = lo[t & 15] ^ hi[t >> 4]  (the swizzle is XOR-linear and the two
-// halves deposit disjoint bits), so a thread finds its sub-cube with two broadcast-free LDS instead of ~40 ALU ops.
+// halves deposit disjoint bits), so a thread finds its representative with two LDS instead of ~40 ALU ops.
 constexpr uint32_t kRBlockUnits = 8;
 
 // ---- record stream (16-byte units) ----------------------------------------------------------------------------
@@ -82,7 +92,12 @@ QC_HD inline uint32_t meta_kind(uint32_t m) { return (m >> 6) & 3u; }
 QC_HD inline uint32_t meta_mode(uint32_t m) { return (m >> 8) & 3u; }
 QC_HD inline uint32_t meta_slot(uint32_t m) { return (m >> 10) & 3u; }
 QC_HD inline uint32_t meta_count(uint32_t m) { return m >> 16; }
+// A DOT / DIAG record of a parity cube whose terms differ in z on the cube's sixth bit carries TWO weight tables: the
+// representative's sixth bit rho (thread-id bit 6, warp-uniform) selects tab[rho]  (w(E, rho) = A(E) + (-1)^rho B(E)).
+constexpr uint32_t kMetaTwoTables = 1u << 12;
 constexpr uint32_t kDotUnits = 1 + 8;   // header + 16 doubles
+constexpr uint32_t kDot2Units = 1 + 16; // header + 2 x 16 doubles
+QC_HD inline uint32_t dot_units(uint32_t meta) { return (meta & kMetaTwoTables) ? kDot2Units : kDotUnits; }
 constexpr uint32_t kLinEntryUnits = 3;  // 48 bytes
 
 struct Unit16 {
