@@ -292,8 +292,8 @@ HostPlan* build_host_plan(int n, size_t T, const uint64_t* xs, const uint64_t* z
     HostPlan* plan = new HostPlan();
     plan->n = n;
     PlanStats& st = plan->stats;
-    const int tau0 = env_int("QC_K2_TAU", 3);            // first passes only build sub-cubes of >= tau x-masks
-    const int min_gain = env_int("QC_K2_MIN_GAIN", 48);  // ... until a pass would serve fewer x-masks than this
+    const int tau0 = env_int("QC_K2_TAU", 9);            // first passes only build sub-cubes of >= tau x-masks
+    const int min_gain = env_int("QC_K2_MIN_GAIN", 128);  // ... until a pass would serve fewer x-masks than this
 
     // ---- x-groups
     std::vector<XG> xg;
