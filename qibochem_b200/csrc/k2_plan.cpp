@@ -364,6 +364,42 @@ HostPlan* build_host_plan(int n, size_t T, const uint64_t* xs, const uint64_t* z
             }
             S |= 1ull << best_bit;
         }
+        // local search: swap one tile bit for one outside bit while that covers more of the uncovered weight
+        if (env_int("QC_K2_LOCAL_SEARCH", 1)) {
+            auto covered = [&](uint64_t mask) {
+                double w = 0.0;
+                for (uint32_t g : uncovered)
+                    if ((xg[g].x & ~mask) == 0) w += xg[g].weight;
+                return w;
+            };
+            double cur = covered(S);
+            for (int iter = 0; iter < 4; ++iter) {
+                bool improved = false;
+                for (int out = 1; out < n; ++out) {
+                    if (!((S >> out) & 1ull)) continue;
+                    // only x-masks that miss exactly one bit can be gained by one swap: count gains per incoming bit
+                    const uint64_t S1 = S & ~(1ull << out);
+                    double lost = 0.0, gain[64] = {0.0};
+                    for (uint32_t g : uncovered) {
+                        const uint64_t miss = xg[g].x & ~S1;
+                        if (miss == 0) continue;  // covered with or without `out`
+                        if (miss == (1ull << out)) lost += xg[g].weight;
+                        else if ((miss & (miss - 1)) == 0) gain[__builtin_ctzll(miss)] += xg[g].weight;
+                    }
+                    int best_in = -1;
+                    double best_gain = lost;
+                    for (int in = 1; in < n; ++in)
+                        if (!((S >> in) & 1ull) && gain[in] > best_gain) best_gain = gain[in], best_in = in;
+                    if (best_in >= 0) {
+                        S = S1 | (1ull << best_in);
+                        cur += best_gain - lost;
+                        improved = true;
+                    }
+                }
+                if (!improved) break;
+            }
+            (void)cur;
+        }
         int spos[kTileBits];
         {
             uint64_t m = S;
