@@ -257,32 +257,34 @@ struct Cube {
 struct CubeCands {
     std::vector<Cube> parity, unit;
 };
-const CubeCands& cube_candidates() {
-    static CubeCands cc;
-    if (cc.parity.empty()) {
-        for (uint32_t m = 0; m < (1u << kTileBits); ++m) {
-            const int w = popc32(m);
-            if (w != kRBits && w != kRBits + 1) continue;
-            Cube c;
-            c.span_mask = m;
-            int pos[kRBits + 1], np = 0;
-            for (int b = 0; b < kTileBits; ++b)
-                if ((m >> b) & 1u) pos[np++] = b;
-            for (int j = 0; j < kRBits; ++j) {
-                c.coord[j] = pos[j];
-                c.gens[j] = (1u << pos[j]) | (w == kRBits + 1 ? (1u << pos[kRBits]) : 0u);
-            }
-            int nr = 0;
-            for (int b = 0; b < kTileBits; ++b)
-                if (!((m >> b) & 1u)) c.rest[nr++] = b;
-            if (w == kRBits + 1) c.rest[nr++] = pos[kRBits];  // the sixth bit: set by the thread id, flipped by odd elements
-            bool res[3] = {false, false, false};
-            for (int j = 0; j < nr; ++j)
-                if (!(w == kRBits + 1 && c.rest[j] == pos[kRBits])) res[c.rest[j] % 3] = true;  // lanes never map to the sixth bit
-            c.conflict_free = res[0] && res[1] && res[2];
-            (w == kRBits ? cc.unit : cc.parity).push_back(c);
+CubeCands make_cube_candidates() {
+    CubeCands cc;
+    for (uint32_t m = 0; m < (1u << kTileBits); ++m) {
+        const int w = popc32(m);
+        if (w != kRBits && w != kRBits + 1) continue;
+        Cube c;
+        c.span_mask = m;
+        int pos[kRBits + 1], np = 0;
+        for (int b = 0; b < kTileBits; ++b)
+            if ((m >> b) & 1u) pos[np++] = b;
+        for (int j = 0; j < kRBits; ++j) {
+            c.coord[j] = pos[j];
+            c.gens[j] = (1u << pos[j]) | (w == kRBits + 1 ? (1u << pos[kRBits]) : 0u);
         }
+        int nr = 0;
+        for (int b = 0; b < kTileBits; ++b)
+            if (!((m >> b) & 1u)) c.rest[nr++] = b;
+        if (w == kRBits + 1) c.rest[nr++] = pos[kRBits];  // the sixth bit: set by the thread id, flipped by odd elements
+        bool res[3] = {false, false, false};
+        for (int j = 0; j < nr; ++j)
+            if (!(w == kRBits + 1 && c.rest[j] == pos[kRBits])) res[c.rest[j] % 3] = true;  // lanes never map to the sixth bit
+        c.conflict_free = res[0] && res[1] && res[2];
+        (w == kRBits ? cc.unit : cc.parity).push_back(c);
     }
+    return cc;
+}
+const CubeCands& cube_candidates() {
+    static const CubeCands cc = make_cube_candidates();  // thread-safe one-time initialisation
     return cc;
 }
 
