@@ -285,18 +285,20 @@ constexpr int kMaxPhaseRuns = 16;
 constexpr int kPhaseTable = 16;  // (cos, sin) entries per run staged in shared memory (support <= 4 bits)
 
 struct PhaseRun {
-    uint64_t x;          // pairing mask (0 => diagonal run)
     uint64_t z0;         // z-mask of the run's first string
     uint64_t sup_mask;   // union support of z_k ^ z_0, pair bit removed (table index = its bits of the canonical element)
-    uint32_t table_off;  // first table entry (double2 units)
-    int8_t hb;           // highest set bit of x (-1 if x == 0)
+    uint32_t table_off;  // first (cos, sin) entry (double2 units)
+    uint32_t kx;         // key of the pairing mask x itself | swap flag (see sel)
+    int8_t hb;           // highest set bit of x (-1 if x == 0: diagonal run)
     int8_t basis;        // which basis vector x is (-1 for a diagonal run)
     int8_t ma;           // a' = c a + f (-i)^ma b,  b' = c b + f (-i)^(2-ma) a   for the pair (a = hb clear, b)
-    int8_t pad;
-    // Index / sign / orientation of a pair are XOR-linear in the element's index c ^ elem[e].  The parts that do not
-    // depend on the thread are tabulated per run for both values h of the representative's orientation bit
-    // (bit hb of c):  sel[h][e] = table-index part (bits 0..3) | sign-parity part (bit 4) | swap flag (bit 5)
-    uint8_t sel[2][32];
+    int8_t pad[5];
+    // A pair's table index, sign parity and orientation are XOR-linear in the element's index c ^ elem[e] -- also
+    // through the "canonical element = the one with bit hb clear" rule, because substituting e ^ x XORs a constant
+    // (kx).  key = table index (bits 0..3) | sign parity (bit 4) | swap flag (bit 5);  key(thread, e) = ckey ^ sel[e]
+    // with ckey from the thread's representative.  Butterfly runs use sel[j], j = 0..15 = the j-th element with the
+    // run's basis bit clear; diagonal runs use all 32.
+    uint8_t sel[32];
 };
 struct PhaseDesc {
     uint64_t elem[kOrbitSize];  // index offset of register element e relative to the thread's first representative
@@ -306,47 +308,64 @@ struct PhaseDesc {
     PhaseRun run[kMaxPhaseRuns];
 };
 
-// (gr + i gi) * v
-__device__ __forceinline__ double2 cmul2(double gr, double gi, double2 v) {
-    return make_double2(gr * v.x - gi * v.y, gr * v.y + gi * v.x);
-}
+constexpr int kKeyTable = 64;  // per run: (cos, signed sin) for every key
 
-// Run on basis vector I: element e (bit I clear) pairs with e | 1 << I.  ODD = ma is odd (w = -+i), else w = +-1.
-// c_hb / c_idx / c_par: orientation bit, table index and sign parity of the thread's representative c (per run).
+// Run on basis vector I: the j-th element e with bit I clear pairs with e | 1 << I.  ODD = ma is odd (w = -+i), else
+// w = +-1.  tb = the run's key table, sl = its 16 selector words (byte offsets into tb), ck = the thread's key << 4.
+// All sign handling lives in the table, so a pair costs one LOP, one LDS.128 and 8 FP64 instructions.
 template <int I, bool ODD>
-__device__ __forceinline__ void orbit_butterfly(double2 (&a)[kOrbitSize], const PhaseRun& d, const double2* __restrict__ tab,
-                                                uint32_t c_hb, uint32_t c_idx, uint32_t c_par, double wsign) {
+__device__ __forceinline__ void orbit_butterfly(double2 (&a)[kOrbitSize], const char* __restrict__ tb,
+                                                const uint4* __restrict__ sl, uint32_t ck) {
 #pragma unroll
-    for (int e = 0; e < kOrbitSize; ++e) {
-        if (e & (1 << I)) continue;
-        const int e1 = e | (1 << I);
-        const uint32_t v = c_hb ? d.sel[1][e] : d.sel[0][e];  // two warp-uniform bytes, picked per thread
-        const uint32_t sw = v & 32u;                         // a[e] is the partner (highest x bit set), a[e1] canonical
-        const double2 cs = tab[c_idx ^ (v & 15u)];
-        const double f = ((c_par ^ (v >> 4)) & 1u) ? -cs.y : cs.y;
-        const double2 u0 = a[e], u1 = a[e1];
-        if (!ODD) {
-            // w = wsign (+-1): canonical a' = c a + f w b, b' = c b - f w a; roles swap with sw
-            const double g = sw ? -f * wsign : f * wsign;
-            a[e] = make_double2(fma(g, u1.x, cs.x * u0.x), fma(g, u1.y, cs.x * u0.y));
-            a[e1] = make_double2(fma(-g, u0.x, cs.x * u1.x), fma(-g, u0.y, cs.x * u1.y));
-        } else {
-            // w = i wsign: a' = c a + i g b and b' = c b + i g a (the same g for both, whatever the orientation)
-            const double g = f * wsign;
-            a[e] = make_double2(fma(-g, u1.y, cs.x * u0.x), fma(g, u1.x, cs.x * u0.y));
-            a[e1] = make_double2(fma(-g, u0.y, cs.x * u1.x), fma(g, u0.x, cs.x * u1.y));
+    for (int q = 0; q < 4; ++q) {
+        const uint4 s4 = sl[q];
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+            const int j = 4 * q + jj;
+            const int e = ((j >> I) << (I + 1)) | (j & ((1 << I) - 1));
+            const int e1 = e | (1 << I);
+            const uint32_t sj = jj == 0 ? s4.x : jj == 1 ? s4.y : jj == 2 ? s4.z : s4.w;
+            const double2 cs = *reinterpret_cast<const double2*>(tb + (sj ^ ck));
+            const double c = cs.x, g = cs.y;
+            const double2 u0 = a[e], u1 = a[e1];
+            if (!ODD) {
+                // a' = c a + g b, b' = c b - g a   (g carries w, the sign parity and the orientation)
+                a[e] = make_double2(fma(g, u1.x, c * u0.x), fma(g, u1.y, c * u0.y));
+                a[e1] = make_double2(fma(-g, u0.x, c * u1.x), fma(-g, u0.y, c * u1.y));
+            } else {
+                // a' = c a + i g b, b' = c b + i g a   (the same for both orientations)
+                a[e] = make_double2(fma(-g, u1.y, c * u0.x), fma(g, u1.x, c * u0.y));
+                a[e1] = make_double2(fma(-g, u0.y, c * u1.x), fma(g, u0.x, c * u1.y));
+            }
         }
     }
 }
 
 __global__ void __launch_bounds__(kOrbitThreads, 2)
     rot_orbit_kernel(double2* __restrict__ psi, uint64_t n_threads_total, const PhaseDesc ph, const double2* __restrict__ table) {
-    __shared__ double2 stab[kMaxPhaseRuns * kPhaseTable];
-    for (int e = threadIdx.x; e < ph.n_runs * kPhaseTable; e += kOrbitThreads) {
-        const PhaseRun& d = ph.run[e / kPhaseTable];
-        const int k = e % kPhaseTable;
-        if (k < (1 << __popcll(d.sup_mask))) stab[e] = __ldg(&table[d.table_off + k]);
+    __shared__ __align__(16) double2 stab[kMaxPhaseRuns * kKeyTable];
+    __shared__ __align__(16) uint32_t ssel[kMaxPhaseRuns * kOrbitSize];
+    for (int e = threadIdx.x; e < ph.n_runs * kKeyTable; e += kOrbitThreads) {
+        const PhaseRun& d = ph.run[e / kKeyTable];
+        const uint32_t key = (uint32_t)e % kKeyTable, idx = key & 15u, par = (key >> 4) & 1u, sw = key >> 5;
+        double2 out = make_double2(0.0, 0.0);
+        if (idx < (1u << __popcll(d.sup_mask))) {
+            const double2 cs = __ldg(&table[d.table_off + idx]);
+            double g;
+            if (d.basis < 0) {
+                g = par ? cs.y : -cs.y;  // multiply by (c - i s0 s): a' = (c v.x - g v.y, c v.y + g v.x)
+            } else {
+                // w = (-i)^ma: +1, -i, -1, +i
+                const double wsign = (d.ma == 0 || d.ma == 3) ? 1.0 : -1.0;
+                g = (par ? -cs.y : cs.y) * wsign;
+                if (!(d.ma & 1) && sw) g = -g;  // roles of a and b swap with the orientation
+            }
+            out = make_double2(cs.x, g);
+        }
+        stab[e] = out;
     }
+    for (int e = threadIdx.x; e < ph.n_runs * kOrbitSize; e += kOrbitThreads)
+        ssel[e] = (uint32_t)ph.run[e / kOrbitSize].sel[e % kOrbitSize] << 4;
     __syncthreads();
     for (uint64_t tg = (uint64_t)blockIdx.x * kOrbitThreads + threadIdx.x; tg < n_threads_total;
          tg += (uint64_t)gridDim.x * kOrbitThreads) {
@@ -357,37 +376,40 @@ __global__ void __launch_bounds__(kOrbitThreads, 2)
         for (int e = 0; e < kOrbitSize; ++e) a[e] = psi[c0 ^ ph.elem[e]];
         for (int r = 0; r < ph.n_runs; ++r) {
             const PhaseRun& d = ph.run[r];
-            const double2* tab = stab + r * kPhaseTable;
+            uint32_t ck = (d.sup_mask ? gather_bits(c0, d.sup_mask) : 0u) | (((uint32_t)__popcll(c0 & d.z0) & 1u) << 4);
+            if (d.hb >= 0 && ((c0 >> d.hb) & 1ull)) ck ^= d.kx;
+            ck <<= 4;
+            const char* tb = reinterpret_cast<const char*>(stab + r * kKeyTable);
+            const uint4* sl = reinterpret_cast<const uint4*>(ssel + r * kOrbitSize);
             if (d.basis < 0) {
 #pragma unroll
-                for (int e = 0; e < kOrbitSize; ++e) {
-                    const uint64_t s = c0 ^ ph.elem[e];
-                    const double2 cs = tab[d.sup_mask ? gather_bits(s, d.sup_mask) : 0u];
-                    const double ms = (__popcll(s & d.z0) & 1) ? cs.y : -cs.y;  // multiply by (c - i s0 s)
-                    const double2 v = a[e];
-                    a[e] = make_double2(cs.x * v.x - ms * v.y, cs.x * v.y + ms * v.x);
+                for (int q = 0; q < 8; ++q) {
+                    const uint4 s4 = sl[q];
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        const int e = 4 * q + jj;
+                        const uint32_t sj = jj == 0 ? s4.x : jj == 1 ? s4.y : jj == 2 ? s4.z : s4.w;
+                        const double2 cs = *reinterpret_cast<const double2*>(tb + (sj ^ ck));
+                        const double2 v = a[e];
+                        a[e] = make_double2(fma(-cs.y, v.y, cs.x * v.x), fma(cs.y, v.x, cs.x * v.y));
+                    }
                 }
                 continue;
             }
-            // w = (-i)^ma: +1, -i, -1, +i
-            const double wsign = (d.ma == 0 || d.ma == 3) ? 1.0 : -1.0;
-            const uint32_t c_hb = (uint32_t)(c0 >> d.hb) & 1u;
-            const uint32_t c_idx = d.sup_mask ? gather_bits(c0, d.sup_mask) : 0u;
-            const uint32_t c_par = (uint32_t)__popcll(c0 & d.z0) & 1u;
-#define QC_BFLY(I)                                                                  \
-    case I:                                                                         \
-        if (d.ma & 1)                                                               \
-            orbit_butterfly<I, true>(a, d, tab, c_hb, c_idx, c_par, wsign);         \
-        else                                                                        \
-            orbit_butterfly<I, false>(a, d, tab, c_hb, c_idx, c_par, wsign);        \
+#define QC_BFLY(I)                                      \
+    case I:                                             \
+        if (d.ma & 1)                                   \
+            orbit_butterfly<I, true>(a, tb, sl, ck);    \
+        else                                            \
+            orbit_butterfly<I, false>(a, tb, sl, ck);   \
         break;
             switch (d.basis) {
                 QC_BFLY(0) QC_BFLY(1) QC_BFLY(2) QC_BFLY(3)
                 default:
                     if (d.ma & 1)
-                        orbit_butterfly<4, true>(a, d, tab, c_hb, c_idx, c_par, wsign);
+                        orbit_butterfly<4, true>(a, tb, sl, ck);
                     else
-                        orbit_butterfly<4, false>(a, d, tab, c_hb, c_idx, c_par, wsign);
+                        orbit_butterfly<4, false>(a, tb, sl, ck);
                     break;
             }
 #undef QC_BFLY
@@ -612,7 +634,6 @@ int apply_rotations_to(qc_state* h, double2* target, size_t R, const uint64_t* x
                 const Run& g = runs[bt.first + k];
                 PhaseRun& pr = pd.run[k];
                 const int ny0 = __builtin_popcountll(g.x & g.z0);
-                pr.x = g.x;
                 pr.z0 = g.z0;
                 pr.sup_mask = g.sup;
                 pr.table_off = table_off[bt.first + k];
@@ -628,14 +649,21 @@ int apply_rotations_to(qc_state* h, double2* target, size_t R, const uint64_t* x
                         if ((v >> __builtin_ctzll(m)) & 1ull) out |= 1u << pos;
                     return out;
                 };
-                const uint32_t xidx = pext(g.x), xpar = (uint32_t)(__builtin_popcountll(g.x & g.z0) & 1);
-                for (int e = 0; e < kOrbitSize; ++e) {
-                    const uint32_t eidx = pext(pd.elem[e]);
-                    const uint32_t epar = (uint32_t)(__builtin_popcountll(pd.elem[e] & g.z0) & 1);
-                    const uint32_t ehb = g.hb >= 0 ? (uint32_t)((pd.elem[e] >> g.hb) & 1ull) : 0u;
-                    for (uint32_t hbit = 0; hbit < 2; ++hbit) {
-                        const uint32_t sw = hbit ^ ehb;  // element e has the highest x bit set: the canonical one is e ^ x
-                        pr.sel[hbit][e] = (uint8_t)((eidx ^ (sw ? xidx : 0u)) | ((epar ^ (sw & xpar)) << 4) | (sw << 5));
+                // key of an index v: table-index bits | sign parity << 4, XOR kx when bit hb of v is set (the
+                // canonical element is then v ^ x; bit 5 of kx records the swap)
+                pr.kx = g.hb >= 0 ? (pext(g.x) | ((uint32_t)(__builtin_popcountll(g.x & g.z0) & 1) << 4) | 32u) : 0u;
+                auto key_of = [&](uint64_t v) {
+                    uint32_t key = pext(v) | ((uint32_t)(__builtin_popcountll(v & g.z0) & 1) << 4);
+                    if (g.hb >= 0 && ((v >> g.hb) & 1ull)) key ^= pr.kx;
+                    return key;
+                };
+                if (pr.basis < 0) {
+                    for (int e = 0; e < kOrbitSize; ++e) pr.sel[e] = (uint8_t)key_of(pd.elem[e]);
+                } else {
+                    const int I = pr.basis;
+                    for (int j = 0; j < kOrbitSize / 2; ++j) {
+                        const int e = ((j >> I) << (I + 1)) | (j & ((1 << I) - 1));
+                        pr.sel[j] = (uint8_t)key_of(pd.elem[e]);
                     }
                 }
             }
