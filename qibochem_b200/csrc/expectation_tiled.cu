@@ -90,6 +90,33 @@ __device__ __forceinline__ double dot_pairs(const double2 (&a)[32], const double
     return (w[0] + w[1]) + (w[2] + w[3]);
 }
 
+// The same as dot_pairs<XR, false> but leaves the four partial sums to the caller, which folds them one record later
+// (the dependent tail of a record then overlaps the products of the next one).
+template <int XR>
+__device__ __forceinline__ void dot_pairs4(const double2 (&a)[32], const double2* __restrict__ tab, double (&w)[4]) {
+    constexpr int HB = XR >= 16 ? 16 : XR >= 8 ? 8 : XR >= 4 ? 4 : XR >= 2 ? 2 : 1;
+    w[0] = w[1] = w[2] = w[3] = 0.0;
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+        double2 t[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) t[j] = tab[4 * b + j];
+        double pr[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int p = pair_index<HB>(8 * b + j);
+            pr[j] = a[p].x * a[p ^ XR].x;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int p = pair_index<HB>(8 * b + j);
+            pr[j] = fma(a[p].y, a[p ^ XR].y, pr[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) w[j & 3] = fma(pr[j], (j & 1) ? t[j >> 1].y : t[j >> 1].x, w[j & 3]);
+    }
+}
+
 template <int HALF>
 __device__ __forceinline__ double dot_diag(const double2 (&a)[32], const double2* __restrict__ tab) {
     double2 t[8];
@@ -200,20 +227,27 @@ __global__ void __launch_bounds__(kTileThreads, 2)
             const uint32_t rho8 = ((threadIdx.x >> 6) & 1u) * 8u;  // two-table records: units to skip for rho = 1
             // ---- simple quads of this cube (coordinate vectors of weight 4 and 3): straight-line code, no dispatch
             const uint32_t quad_mask = b0.z >> 16;
-#define QC_QUAD(S, XR)                                                                                  \
-    if (quad_mask & (1u << S)) {                                                                        \
-        const uint4 hd = *rp;                                                                           \
-        const uint32_t two = (hd.w >> 12) & 1u;                                                         \
-        const double w = dot_pairs<XR, false>(a, reinterpret_cast<const double2*>(rp + 1 + two * rho8)); \
-        if (S & 1)                                                                                      \
-            acc1 += apply_sign(w, sign_parity(base, org, hd));                                          \
-        else                                                                                            \
-            acc0 += apply_sign(w, sign_parity(base, org, hd));                                          \
-        rp += kDotUnits + two * 8u;                                                                     \
+            // software-pipelined: a slot leaves its four partial sums and its sign pending and the next slot folds
+            // them, so the dependent tail of a record overlaps the products of the next one; the table address of a
+            // record comes from the PREVIOUS header (kMetaNextTwoTables), so its loads do not wait for its own header
+            double pw[4] = {0.0, 0.0, 0.0, 0.0};
+            unsigned psign = 0u;
+            uint32_t two = b0.w & 1u;
+#define QC_QUAD(S, XR)                                                                          \
+    if (quad_mask & (1u << S)) {                                                                \
+        double w4[4];                                                                           \
+        dot_pairs4<XR>(a, reinterpret_cast<const double2*>(rp + 1 + two * rho8), w4);           \
+        const uint4 hd = *rp;                                                                   \
+        acc0 += apply_sign((pw[0] + pw[1]) + (pw[2] + pw[3]), psign);                           \
+        pw[0] = w4[0], pw[1] = w4[1], pw[2] = w4[2], pw[3] = w4[3];                             \
+        psign = sign_parity(base, org, hd);                                                     \
+        rp += kDotUnits + two * 8u;                                                             \
+        two = (hd.w >> 13) & 1u;                                                                \
     }
             QC_QUAD(0, 30) QC_QUAD(1, 29) QC_QUAD(2, 27) QC_QUAD(3, 23) QC_QUAD(4, 15)
             QC_QUAD(5, 7) QC_QUAD(6, 11) QC_QUAD(7, 13) QC_QUAD(8, 14) QC_QUAD(9, 19)
             QC_QUAD(10, 21) QC_QUAD(11, 22) QC_QUAD(12, 25) QC_QUAD(13, 26) QC_QUAD(14, 28)
+            acc1 += apply_sign((pw[0] + pw[1]) + (pw[2] + pw[3]), psign);
 #undef QC_QUAD
             // ---- generic records
             double A0 = 0.0, A1 = 0.0, A2 = 0.0, A3 = 0.0;

@@ -505,6 +505,25 @@ HostPlan* build_host_plan(int n, size_t T, const uint64_t* xs, const uint64_t* z
                 rb.hdr.rec_off = rec_off;
                 rec_off += (uint32_t)rb.recs.size();
                 for (int j = 0; j < kQuadSlots; ++j) rec_off += (uint32_t)rb.quads[j].size();
+                {   // every quad record announces whether the NEXT one carries two tables (the first: the visit header)
+                    Unit16* prev = nullptr;
+                    rb.hdr.pad = 0;
+                    for (int j = 0; j < kQuadSlots; ++j) {
+                        if (rb.quads[j].empty()) continue;
+                        TRecHdr h;
+                        memcpy(&h, &rb.quads[j][0], sizeof(h));
+                        const bool two = (h.meta & kMetaTwoTables) != 0;
+                        if (prev) {
+                            TRecHdr ph;
+                            memcpy(&ph, prev, sizeof(ph));
+                            ph.meta = two ? (ph.meta | kMetaNextTwoTables) : (ph.meta & ~kMetaNextTwoTables);
+                            memcpy(prev, &ph, sizeof(ph));
+                        } else if (two) {
+                            rb.hdr.pad = 1;
+                        }
+                        prev = &rb.quads[j][0];
+                    }
+                }
                 push_units(plan->units, &rb.hdr, sizeof(TRBlock));
                 uint32_t origin[24];  // lo[16] from thread bits 0..3, hi[8] from thread bits 4..6
                 for (uint32_t t = 0; t < 24; ++t) {

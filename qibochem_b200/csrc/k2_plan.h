@@ -52,7 +52,7 @@ struct TRBlock {           // 32 bytes = 2 units, followed by 6 units of origin 
     uint16_t sbit[kRBits]; // swizzled tile slot offset of each generator (the swizzle is XOR-linear)
     uint16_t quad_mask;    // bit s: the visit starts with a plain DOT/ACC/Re record for xr = kQuadKappa[s] ("simple
                            // quad"), in ascending s -- the kernel runs these from straight-line code without dispatch
-    uint32_t pad;
+    uint32_t pad;          // bit 0: the first quad record carries two tables
     uint32_t rec_off;      // first record (quad records first), in units from the start of the blob
     uint32_t n_recs;       // generic records following the popcount(quad_mask) quad records
     uint32_t n_groups;
@@ -95,6 +95,9 @@ QC_HD inline uint32_t meta_count(uint32_t m) { return m >> 16; }
 // A DOT / DIAG record of a parity cube whose terms differ in z on the cube's sixth bit carries TWO weight tables: the
 // representative's sixth bit rho (thread-id bit 6, warp-uniform) selects tab[rho]  (w(E, rho) = A(E) + (-1)^rho B(E)).
 constexpr uint32_t kMetaTwoTables = 1u << 12;
+// Set on a simple-quad record when the NEXT quad record of the visit carries two tables (TRBlock::pad bit 0 says it
+// for the first one): the kernel then knows a record's table address before it has loaded the record's own header.
+constexpr uint32_t kMetaNextTwoTables = 1u << 13;
 constexpr uint32_t kDotUnits = 1 + 8;   // header + 16 doubles
 constexpr uint32_t kDot2Units = 1 + 16; // header + 2 x 16 doubles
 QC_HD inline uint32_t dot_units(uint32_t meta) { return (meta & kMetaTwoTables) ? kDot2Units : kDotUnits; }
