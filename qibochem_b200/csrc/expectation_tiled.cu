@@ -133,6 +133,39 @@ __device__ __forceinline__ double dot_diag(const double2 (&a)[32], const double2
     return (w[0] + w[1]) + (w[2] + w[3]);
 }
 
+// HOP record (k2_plan.h): three tables weight the same 16 products; two accumulators per table => six independent chains
+template <int XR>
+__device__ __forceinline__ void dot3(const double2 (&a)[32], const double2* __restrict__ tab_acc,
+                                     const double2* __restrict__ tab_pat, double& w_acc, double& A0, double& A1) {
+    constexpr int HB = XR >= 16 ? 16 : XR >= 8 ? 8 : XR >= 4 ? 4 : XR >= 2 ? 2 : 1;
+    double w[3][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+        double pr[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int p = pair_index<HB>(8 * b + j);
+            pr[j] = a[p].x * a[p ^ XR].x;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int p = pair_index<HB>(8 * b + j);
+            pr[j] = fma(a[p].y, a[p ^ XR].y, pr[j]);
+        }
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+            double2 tt[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) tt[j] = t == 0 ? tab_acc[4 * b + j] : tab_pat[8 * (t - 1) + 4 * b + j];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) w[t][j & 1] = fma(pr[j], (j & 1) ? tt[j >> 1].y : tt[j >> 1].x, w[t][j & 1]);
+        }
+    }
+    w_acc = w[0][0] + w[0][1];
+    A0 = w[1][0] + w[1][1];
+    A1 = w[2][0] + w[2][1];
+}
+
 // sel = xr | im << 5 for DOT records; 0 / 32 = lower / upper half of a diagonal record.  All 64 values are cases, so
 // the switch compiles to ONE jump table.
 __device__ __forceinline__ double dot_dispatch(uint32_t sel, const double2 (&a)[32], const double2* __restrict__ tab) {
@@ -155,6 +188,33 @@ __device__ __forceinline__ double dot_dispatch(uint32_t sel, const double2 (&a)[
 __device__ __forceinline__ unsigned sign_parity(uint64_t base, uint32_t org, const uint4& hd) {
     const uint32_t lo = (uint32_t)base & hd.x, hi = (uint32_t)(base >> 32) & hd.y;
     return (unsigned)__popc(lo ^ hi ^ (org & hd.z));
+}
+
+// One HOP record: ACC table + two pattern sums combined by 32-byte entries; returns the next record
+template <int XR>
+__device__ __forceinline__ const uint4* hop_record(const double2 (&a)[32], const uint4* __restrict__ rp, uint64_t base,
+                                                   uint32_t org, uint32_t rho, double& acc0, double& acc1) {
+    const uint4 hd = *rp;
+    double w, A0, A1;
+    const uint32_t two8 = (hd.w & kMetaTwoTables) ? 8u : 0u;  // the ACC table for rho = 1 follows the pattern tables
+    dot3<XR>(a, reinterpret_cast<const double2*>((two8 && rho) ? rp + kHopHeadUnits : rp + 1),
+             reinterpret_cast<const double2*>(rp + 9), w, A0, A1);
+    if ((hd.w & kMetaHopFlip0) && rho) A0 = -A0;
+    if ((hd.w & kMetaHopFlip1) && rho) A1 = -A1;
+    acc0 += apply_sign(w, sign_parity(base, org, hd));
+    const uint32_t cnt = meta_count(hd.w);
+    const uint4* ep = rp + kHopHeadUnits + two8;
+#pragma unroll 2
+    for (uint32_t e = 0; e < cnt; ++e, ep += kHopEntryUnits) {
+        const uint4 eh = ep[0];
+        const double2 c = *reinterpret_cast<const double2*>(ep + 1);
+        const double v = fma(c.x, A0, c.y * A1);
+        if (e & 1u)
+            acc1 += apply_sign(v, sign_parity(base, org, eh));
+        else
+            acc0 += apply_sign(v, sign_parity(base, org, eh));
+    }
+    return ep;
 }
 
 // One CTA = 128 threads, 64 KB tile + the pass's blob (sub-cube headers + records, <= 44 KB) in shared memory;
@@ -206,7 +266,7 @@ __global__ void __launch_bounds__(kTileThreads, 2)
 
         for (uint32_t rb = 0; rb < pass.n_rblocks; ++rb) {
             const uint4 b0 = blob[rb * kRBlockUnits];      // sbit[0..4], quad_mask
-            const uint4 b1 = blob[rb * kRBlockUnits + 1];  // rec_off, n_recs, n_groups
+            const uint4 b1 = blob[rb * kRBlockUnits + 1];  // rec_off, n_recs, n_groups, hop_mask
             // tile-local origin of this thread's sub-cube (and its swizzled slot) from the visit's two origin tables
             const uint32_t* otab = reinterpret_cast<const uint32_t*>(blob + rb * kRBlockUnits + 2);
             const uint32_t packed = otab[threadIdx.x & 15u] ^ otab[16u + (threadIdx.x >> 4)];
@@ -249,6 +309,16 @@ __global__ void __launch_bounds__(kTileThreads, 2)
             QC_QUAD(10, 21) QC_QUAD(11, 22) QC_QUAD(12, 25) QC_QUAD(13, 26) QC_QUAD(14, 28)
             acc1 += apply_sign((pw[0] + pw[1]) + (pw[2] + pw[3]), psign);
 #undef QC_QUAD
+            // ---- HOP records (weight-2 x-masks): straight-line code per coordinate vector
+            if (GENERIC && b1.w) {
+                const uint32_t hop_mask = b1.w, rho = (threadIdx.x >> 6) & 1u;
+#define QC_HOP(S, XR) \
+    if (hop_mask & (1u << S)) rp = hop_record<XR>(a, rp, base, org, rho, acc0, acc1);
+                QC_HOP(0, 1) QC_HOP(1, 2) QC_HOP(2, 4) QC_HOP(3, 8) QC_HOP(4, 16)
+                QC_HOP(5, 3) QC_HOP(6, 5) QC_HOP(7, 6) QC_HOP(8, 9) QC_HOP(9, 10)
+                QC_HOP(10, 12) QC_HOP(11, 17) QC_HOP(12, 18) QC_HOP(13, 20) QC_HOP(14, 24)
+#undef QC_HOP
+            }
             // ---- generic records
             double A0 = 0.0, A1 = 0.0, A2 = 0.0, A3 = 0.0;
             for (uint32_t r = 0; GENERIC && r < b1.y; ++r) {

@@ -78,6 +78,13 @@ struct LinEntry {
     uint32_t pad;
     double c[kSlots];
 };
+struct HopEntry {
+    uint64_t z_outer;
+    uint32_t z_rest;
+    uint32_t pad;
+    double c[2];
+};
+static_assert(sizeof(HopEntry) == 16 * kHopEntryUnits, "record layout");
 static_assert(sizeof(DotRec) == 16 * kDotUnits, "record layout");
 static_assert(sizeof(LinEntry) == 16 * kLinEntryUnits, "record layout");
 
@@ -89,6 +96,7 @@ struct Atom {
     uint32_t n_recs = 0;
     bool needs_setup = false;
     int quad_slot = -1;  // j when this is the single record of a "simple quad" (xr = 31 ^ (1 << j))
+    int hop_slot = -1;   // s when this is a HOP record (xr = kHopKappa[s])
 };
 struct GroupRecs {
     std::vector<Unit16> setup;
@@ -178,6 +186,70 @@ GroupRecs emit_group(const XG& g, const uint64_t* zs, const double* cs, uint64_t
         push_units(units, tab0, 16 * sizeof(double));
         if (tab1) push_units(units, tab1, 16 * sizeof(double));
     };
+    // ---- HOP record: pattern sums on at most two slots + at most one table of its own, all real, xr of weight <= 2
+    {
+        int hop_slot = -1;
+        for (int sl = 0; sl < kHopSlots; ++sl)
+            if (kHopKappa[sl] == xr) hop_slot = sl;
+        int used[kSlots], n_used = 0;
+        bool ok = hop_slot >= 0 && rho_pos >= 0 && !lin_subs.empty() && tab_subs.size() <= 1 && lin_subs.size() <= 1200;
+        for (size_t j = 0; ok && j < by_freq.size(); ++j)
+            if (slot_used[j]) {
+                if (n_used == 2 || by_freq[j].second.second != 0) ok = false;
+                else used[n_used++] = (int)j;
+            }
+        bool any0 = false, any1 = false;
+        if (ok && tab_subs.size() == 1) {
+            for (const Term& tm : *tab_subs[0]) ((tm.pk & 32u) ? any1 : any0) = true;
+            if (tab_keys[0].second != 0) ok = false;
+        }
+        if (ok) {
+            Atom atom;
+            atom.hop_slot = hop_slot;
+            atom.n_recs = 1;
+            uint32_t meta = rec_meta(xr, 0, kRecDot, kModeHop, 0, (uint32_t)lin_subs.size());
+            double tabs[3][16], tab_rho1[16];
+            for (int t = 0; t < 3; ++t)
+                for (int k = 0; k < 16; ++k) tabs[t][k] = 0.0;
+            for (int k = 0; k < 16; ++k) tab_rho1[k] = 0.0;
+            uint64_t key = 0;
+            const bool two = any0 && any1;  // mixed: the representative's sixth bit selects the ACC table
+            if (tab_subs.size() == 1) {
+                key = tab_keys[0].first | ((any1 && !any0) ? rho_bit : 0ull);
+                double pat[16];
+                for (const Term& tm : *tab_subs[0]) {
+                    pattern_table(xr, tm.pk & 31u, 0, pair_scale * tm.d, pat);
+                    const double s1 = ((tm.pk & 32u) && any0) ? -1.0 : 1.0;
+                    for (int k = 0; k < 16; ++k) tabs[0][k] += pat[k], tab_rho1[k] += s1 * pat[k];
+                }
+            }
+            if (two) meta |= kMetaTwoTables;
+            for (int j = 0; j < n_used; ++j) {
+                const uint32_t pk = by_freq[used[j]].second.first;
+                pattern_table(xr, pk & 31u, 0, pair_scale, tabs[1 + j]);
+                if (pk & 32u) meta |= j == 0 ? kMetaHopFlip0 : kMetaHopFlip1;
+            }
+            const TRecHdr h = header(key, meta);
+            push_units(atom.units, &h, sizeof(h));
+            push_units(atom.units, tabs, sizeof(tabs));
+            if (two) push_units(atom.units, tab_rho1, sizeof(tab_rho1));
+            for (size_t i = 0; i < lin_subs.size(); ++i) {
+                HopEntry e;
+                memset(&e, 0, sizeof(e));
+                const TRecHdr eh = header(lin_keys[i].first, 0);
+                e.z_outer = eh.z_outer;
+                e.z_rest = eh.z_rest;
+                for (const Term& tm : *lin_subs[i]) {
+                    const int sl = slot_of(tm.pk, tm.odd);
+                    e.c[sl == used[0] ? 0 : 1] += tm.d;
+                }
+                push_units(atom.units, &e, sizeof(e));
+                ++st.n_lin;
+            }
+            out.atoms.push_back(std::move(atom));
+            return out;
+        }
+    }
     // ---- pattern sums A[slot]
     if (!lin_subs.empty()) {
         for (size_t j = 0; j < by_freq.size(); ++j) {
@@ -485,6 +557,7 @@ HostPlan* build_host_plan(int n, size_t T, const uint64_t* xs, const uint64_t* z
             TRBlock hdr;
             int perm[kTileBits - kRBits];  // thread-id bit j -> tile position
             std::vector<Unit16> quads[kQuadSlots];  // simple-quad records by slot
+            std::vector<Unit16> hops[kHopSlots];    // HOP records by slot
             std::vector<Unit16> recs;           // generic records
         };
         std::vector<RB> cur;       // sub-cube visits of the pass being assembled
@@ -501,10 +574,11 @@ HostPlan* build_host_plan(int n, size_t T, const uint64_t* xs, const uint64_t* z
             pass.n_groups = cur_groups;
             uint32_t rec_off = (uint32_t)cur.size() * kRBlockUnits;
             for (RB& rb : cur) {
-                pass.n_generic += rb.hdr.n_recs;
+                pass.n_generic += rb.hdr.n_recs + (uint32_t)popc32(rb.hdr.hop_mask);
                 rb.hdr.rec_off = rec_off;
                 rec_off += (uint32_t)rb.recs.size();
                 for (int j = 0; j < kQuadSlots; ++j) rec_off += (uint32_t)rb.quads[j].size();
+                for (int j = 0; j < kHopSlots; ++j) rec_off += (uint32_t)rb.hops[j].size();
                 {   // every quad record announces whether the NEXT one carries two tables (the first: the visit header)
                     Unit16* prev = nullptr;
                     rb.hdr.pad = 0;
@@ -538,6 +612,8 @@ HostPlan* build_host_plan(int n, size_t T, const uint64_t* xs, const uint64_t* z
             for (RB& rb : cur) {
                 for (int j = 0; j < kQuadSlots; ++j)
                     plan->units.insert(plan->units.end(), rb.quads[j].begin(), rb.quads[j].end());
+                for (int j = 0; j < kHopSlots; ++j)
+                    plan->units.insert(plan->units.end(), rb.hops[j].begin(), rb.hops[j].end());
                 plan->units.insert(plan->units.end(), rb.recs.begin(), rb.recs.end());
             }
             pass.blob_units = rec_off;
@@ -628,6 +704,9 @@ HostPlan* build_host_plan(int n, size_t T, const uint64_t* xs, const uint64_t* z
                     if (atom.quad_slot >= 0 && !((rb.hdr.quad_mask >> atom.quad_slot) & 1u)) {
                         rb.quads[atom.quad_slot] = atom.units;
                         rb.hdr.quad_mask |= (uint16_t)(1u << atom.quad_slot);
+                    } else if (atom.hop_slot >= 0) {  // one x-mask per coordinate vector and visit: the slot is free
+                        rb.hops[atom.hop_slot] = atom.units;
+                        rb.hdr.hop_mask |= 1u << atom.hop_slot;
                     } else {
                         rb.recs.insert(rb.recs.end(), atom.units.begin(), atom.units.end());
                         rb.hdr.n_recs += atom.n_recs;
@@ -722,10 +801,33 @@ double check_host_plan(const HostPlan* plan, size_t T, const uint64_t* xs, const
                     uq += dot_units(h.meta);
                 }
             }
-            for (uint32_t r = 0; r < n_quads + blk.n_recs; ++r) {
+            const uint32_t n_hops = (uint32_t)popc32(blk.hop_mask);
+            if (blk.hop_mask >> kHopSlots) return -1.0;
+            {   // the HOP records follow the quads, in slot order, with the announced coordinate vectors
+                uint32_t uh = u;
+                for (uint32_t r = 0; r < n_quads; ++r) {
+                    TRecHdr h;
+                    memcpy(&h, &plan->units[uh], sizeof(h));
+                    uh += dot_units(h.meta);
+                }
+                for (int sl = 0; sl < kHopSlots; ++sl) {
+                    if (!((blk.hop_mask >> sl) & 1u)) continue;
+                    TRecHdr h;
+                    memcpy(&h, &plan->units[uh], sizeof(h));
+                    if (meta_kind(h.meta) != kRecDot || meta_mode(h.meta) != kModeHop || meta_im(h.meta) != 0 ||
+                        meta_xr(h.meta) != kHopKappa[sl])
+                        return -1.0;
+                    uh += hop_units(h.meta);
+                }
+            }
+            for (uint32_t r = 0; r < n_quads + n_hops + blk.n_recs; ++r) {
                 TRecHdr h;
                 memcpy(&h, &plan->units[u], sizeof(h));
-                const uint32_t units = meta_kind(h.meta) == kRecLin ? 1 + kLinEntryUnits * meta_count(h.meta) : dot_units(h.meta);
+                const bool is_hop = meta_kind(h.meta) == kRecDot && meta_mode(h.meta) == kModeHop;
+                if (is_hop != (r >= n_quads && r < n_quads + n_hops)) return -1.0;
+                const uint32_t units = is_hop ? hop_units(h.meta)
+                                              : meta_kind(h.meta) == kRecLin ? 1 + kLinEntryUnits * meta_count(h.meta)
+                                                                             : dot_units(h.meta);
                 uint64_t x = 0;
                 for (int j = 0; j < kRBits; ++j)
                     if ((meta_xr(h.meta) >> j) & 1u) x ^= cg.gen[j];
@@ -818,6 +920,28 @@ double check_host_plan(const HostPlan* plan, size_t T, const uint64_t* xs, const
                             got[a_type[j]] += (par ? -1.0 : 1.0) * le.c[j] * A[j] * (a_type[j] ? flip_im : 1.0);
                     }
                     u += 1 + kLinEntryUnits * meta_count(h.meta);
+                    continue;
+                }
+                if (kind == kRecDot && meta_mode(h.meta) == kModeHop) {
+                    if (k < 0) return -1.0;
+                    const int rho_pos = popc64(cg.gen[0]) == 2 ? 63 - __builtin_clzll(cg.gen[0]) : -1;
+                    if (rho_pos < 0) return -1.0;
+                    const uint32_t rho = (uint32_t)((c >> rho_pos) & 1ull);
+                    double tabs[3][16];
+                    memcpy(tabs, &plan->units[u + 1], sizeof(tabs));
+                    const uint32_t two8 = (h.meta & kMetaTwoTables) ? 8u : 0u;
+                    if (two8 && rho) memcpy(tabs[0], &plan->units[u + kHopHeadUnits], sizeof(tabs[0]));
+                    const int par = (popc64(c & h.z_outer) + popc32(org_local & h.z_rest)) & 1;
+                    got[0] += par ? -tabs[0][k] : tabs[0][k];
+                    const double a0 = tabs[1][k] * (((h.meta & kMetaHopFlip0) && rho) ? -1.0 : 1.0);
+                    const double a1 = tabs[2][k] * (((h.meta & kMetaHopFlip1) && rho) ? -1.0 : 1.0);
+                    for (uint32_t e = 0; e < meta_count(h.meta); ++e) {
+                        HopEntry he;
+                        memcpy(&he, &plan->units[u + kHopHeadUnits + two8 + kHopEntryUnits * e], sizeof(he));
+                        const int pe = (popc64(c & he.z_outer) + popc32(org_local & he.z_rest)) & 1;
+                        got[0] += (pe ? -1.0 : 1.0) * (he.c[0] * a0 + he.c[1] * a1);
+                    }
+                    u += hop_units(h.meta);
                     continue;
                 }
                 DotRec r;

@@ -56,13 +56,26 @@ struct TRBlock {           // 32 bytes = 2 units, followed by 6 units of origin 
     uint32_t rec_off;      // first record (quad records first), in units from the start of the blob
     uint32_t n_recs;       // generic records following the popcount(quad_mask) quad records
     uint32_t n_groups;
-    uint32_t pad2;
+    uint32_t hop_mask;     // bit s: a HOP record for xr = kHopKappa[s] follows the quad records, in ascending s
 };
 static_assert(sizeof(TRBlock) == 32, "TRBlock layout");
 // coordinate vectors with a straight-line path in the kernel: the weight-4 and weight-3 ones (in a parity cube these
 // are exactly the 15 four-bit x-masks: weight 3 means the sixth bit takes part)
 constexpr int kQuadSlots = 15;
 constexpr uint32_t kQuadKappa[kQuadSlots] = {30, 29, 27, 23, 15, 7, 11, 13, 14, 19, 21, 22, 25, 26, 28};
+// HOP record: the x-masks of weight 2 of a molecular Hamiltonian ("hopping" strings X_p Z..Z X_q, Y_p Z..Z Y_q, bare
+// and decorated with one Z_r) need one ACC table plus two pattern sums A0, A1 that many LIN entries combine.  All
+// three tables weight the SAME 16 products, so one record carries them and the kernel forms the products once, from
+// straight-line code selected by hop_mask (xr of weight 1 or 2 in a parity cube):
+//   header (mode kModeHop, count = LIN2 entries; kMetaHopFlip0/1: A_j changes sign with the representative's sixth
+//   bit rho) + 8 units ACC table + 2 x 8 units pattern tables [+ 8 units: the ACC table for rho = 1, kMetaTwoTables]
+//   + count entries of 32 bytes {z_outer, z_rest, pad, c0, c1}:
+//     acc += (-1)^{popc(i & z_hdr)} w_acc  +  sum_e (-1)^{popc(i & z_e)} (c0 A0 + c1 A1)
+constexpr int kHopSlots = 15;
+constexpr uint32_t kHopKappa[kHopSlots] = {1, 2, 4, 8, 16, 3, 5, 6, 9, 10, 12, 17, 18, 20, 24};
+constexpr uint32_t kHopHeadUnits = 1 + 3 * 8;
+constexpr uint32_t kHopEntryUnits = 2;
+constexpr uint32_t kMetaHopFlip0 = 1u << 14, kMetaHopFlip1 = 1u << 15;
 // A sub-cube visit in the blob: TRBlock (2 units) + origin tables (6 units): uint32 lo[16], hi[8] with
 // (origin << 16 | swizzled origin) of thread t = lo[t & 15] ^ hi[t >> 4]  (the swizzle is XOR-linear and the two
 // halves deposit disjoint bits), so a thread finds its representative with two LDS instead of ~40 ALU ops.
@@ -82,7 +95,7 @@ struct TRecHdr {
     uint32_t meta;
 };
 enum : uint32_t { kRecDot = 0, kRecDiagLo = 1, kRecDiagHi = 2, kRecLin = 3 };
-enum : uint32_t { kModeAcc = 0, kModeSet = 1, kModeAdd = 2 };
+enum : uint32_t { kModeAcc = 0, kModeSet = 1, kModeAdd = 2, kModeHop = 3 };
 QC_HD inline uint32_t rec_meta(uint32_t xr, uint32_t im, uint32_t kind, uint32_t mode, uint32_t slot, uint32_t count) {
     return (xr & 31u) | ((im & 1u) << 5) | ((kind & 3u) << 6) | ((mode & 3u) << 8) | ((slot & 3u) << 10) | (count << 16);
 }
@@ -102,6 +115,9 @@ constexpr uint32_t kDotUnits = 1 + 8;   // header + 16 doubles
 constexpr uint32_t kDot2Units = 1 + 16; // header + 2 x 16 doubles
 QC_HD inline uint32_t dot_units(uint32_t meta) { return (meta & kMetaTwoTables) ? kDot2Units : kDotUnits; }
 constexpr uint32_t kLinEntryUnits = 3;  // 48 bytes
+QC_HD inline uint32_t hop_units(uint32_t meta) {
+    return kHopHeadUnits + ((meta & kMetaTwoTables) ? 8u : 0u) + kHopEntryUnits * meta_count(meta);
+}
 
 struct Unit16 {
     uint64_t lo, hi;
