@@ -372,7 +372,8 @@ def measure_full_stream(wl, st, stream):
 
 def k2_fp64_roofline(wl, prof, args):
     """What really bounds the tiled expectation: FP64 issue.  FP64 instructions per pass are counted from the plan
-    (DOT record: 48 DMUL/DFMA + 4 DADD per thread, LIN entry: 4 + 2) and compared with the DFMA rate measured on this
+    (DOT record: 48 DMUL/DFMA + 4 DADD per thread; LIN / HOP entry: counted as 3, the HOP figure, and a HOP head as
+    one DOT record -- both on the low side) and compared with the DFMA rate measured on this
     pool's B200 by tools/ubench/fp64_pipe.cu (profiles/r1_fp64_pipe_b200.txt: 63.4 DFMA/clk/SM = 34.9 TFLOP/s)."""
     import ctypes as C
 
@@ -388,7 +389,7 @@ def k2_fp64_roofline(wl, prof, args):
         return None
     n_pass, n_cubes, n_dot, n_lin = (int(stats[k]) for k in (2, 3, 4, 5))
     threads = 2.0 ** wl["n"] / 32.0  # one thread per 32-amplitude sub-cube
-    fp64_instr = (52.0 * n_dot + 6.0 * n_lin) * threads  # per energy evaluation
+    fp64_instr = (52.0 * n_dot + 3.0 * n_lin) * threads  # per energy evaluation
     seconds = prof["k2_tiled"]["ms"] / 1e3 / args.steps
     peak_instr = 63.4 * 148 * 1.965e9
     return {"unit": "FP64 instr/s (DFMA-rate)", "achieved": fp64_instr / seconds, "peak": peak_instr, "frac": fp64_instr / seconds / peak_instr,
