@@ -394,6 +394,10 @@ def k2_fp64_roofline(wl, prof, args):
     peak_instr = 63.4 * 148 * 1.965e9
     return {"unit": "FP64 instr/s (DFMA-rate)", "achieved": fp64_instr / seconds, "peak": peak_instr, "frac": fp64_instr / seconds / peak_instr,
             "peak_source": "tools/ubench/fp64_pipe.cu on this pool's B200: 63.4 DFMA/clk/SM x 148 SMs x 1.965 GHz (34.9 TFLOP/s)",
+            "operand_bound": {"clk_per_record_and_warp": 146.0, "frac": fp64_instr / 52.0 / 32.0 * 146.0 / (seconds * 148 * 4 * 1.965e9),
+                              "note": "three-register-operand DFMAs take 2.85-3.05 clk per SM sub-partition on B200 and a weight fed by a "
+                                      "broadcast LDS.128 ~4 clk (profiles/r1_fp64_operands_b200.txt): a DOT record costs 142-150 clk per "
+                                      "warp at best; frac = warp-level record-equivalents x 146 clk / (592 SM sub-partitions x clock x time)"},
             "plan": {"hbm_passes": n_pass, "sub_cube_gathers": n_cubes, "dot_records": n_dot, "lin_entries": n_lin},
             "shared_memory_gather_bytes_per_eval": n_cubes * 16.0 * 2.0 ** wl["n"]}  # fmt: skip
 
