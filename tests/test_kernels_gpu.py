@@ -519,6 +519,45 @@ def test_tiled_expectation_random_dense_hamiltonian(DeviceState, n, seed):
         assert abs(st.expectation(xs, zs, cs) - e) < 1e-9 * max(1.0, np.abs(cs).sum() / 50)
 
 
+@pytest.mark.parametrize("n,seed", [(13, 0), (16, 1), (18, 2)])
+def test_tiled_expectation_hopping_groups(DeviceState, n, seed):
+    """Weight-2 x-masks (the HOP record path of the tiled expectation and its fall-backs): for random pairs {p, q}
+    the strings X..X / Y..Y with a shared random Z background, decorated with one or two extra Z (hop-able: two real
+    patterns, many sign-only subgroups), plus groups with X..Y / Y..X strings (odd nY: imaginary patterns), with three
+    Y-patterns and with a handful of terms only (the generic record path); tiles == sweeps == oracle."""
+    from oracle import oracle_c as OC
+
+    rng = np.random.default_rng(100 + seed)
+    bit = lambda q: 1 << q  # noqa: E731
+    xs, zs = [], []
+    pairs = [tuple(sorted(rng.choice(n, size=2, replace=False).tolist())) for _ in range(60)]
+    for k, (p, q) in enumerate(dict.fromkeys(pairs)):
+        x = bit(p) | bit(q)
+        others = [r for r in range(n) if r not in (p, q)]
+        back = int(sum(bit(r) for r in others if rng.random() < 0.4))  # shared Z background (a "chain")
+        ys = [0, x] if k % 4 else [0, x, bit(p), bit(q)]  # every fourth group also has XY / YX strings
+        if k % 7 == 3:
+            ys = [0]  # a single pattern
+        decos = [0] + [bit(r) for r in others] + [bit(a) | bit(b) for a, b in zip(others[::2], others[1::2])]
+        if k % 5 == 4:
+            decos = decos[:3]  # too few subgroups for pattern sums
+        for y in ys:
+            for d in decos:
+                xs.append(x), zs.append(back ^ y ^ d)
+    cs = rng.normal(size=len(xs))
+    psi = random_state(n, 7 + seed)
+    ref = OC.expectation_masks(psi, n, xs, zs, cs)
+    tol = 1e-10 * max(1.0, np.abs(cs).sum() / 50)
+    with DeviceState(n) as st:
+        st.from_numpy(psi)
+        st.set_option("k2_mode", 2)
+        e = st.expectation(xs, zs, cs)
+        assert abs(e - ref) < tol
+        assert e == st.expectation(xs, zs, cs)  # deterministic
+        st.set_option("k2_mode", 1)
+        assert abs(st.expectation(xs, zs, cs) - ref) < tol
+
+
 def test_empty_and_degenerate_inputs(DeviceState):
     """Empty programs / term lists, tile modes requested on registers too small for a tile, repeated identical calls."""
     n = 6
