@@ -301,6 +301,48 @@ def test_k2_tiled_plan_serves_every_xmask_once(native_lib, n, T):
         assert n_pass * 20 < n_x and n_tiled / n_cubes > 2.5
 
 
+def hopping_term_list(n, seed):
+    """Weight-2 x-masks with a shared Z background, decorated with one or two extra Z: the term structure HOP records
+    are made for, plus variants that must fall back to the generic records (odd nY, a single pattern, few subgroups)."""
+    rng = np.random.default_rng(100 + seed)
+    bit = lambda q: 1 << q  # noqa: E731
+    xs, zs = [], []
+    pairs = [tuple(sorted(rng.choice(n, size=2, replace=False).tolist())) for _ in range(60)]
+    for k, (p, q) in enumerate(dict.fromkeys(pairs)):
+        x = bit(p) | bit(q)
+        others = [r for r in range(n) if r not in (p, q)]
+        back = int(sum(bit(r) for r in others if rng.random() < 0.4))
+        ys = [0, x] if k % 4 else [0, x, bit(p), bit(q)]
+        if k % 7 == 3:
+            ys = [0]
+        decos = [0] + [bit(r) for r in others] + [bit(a) | bit(b) for a, b in zip(others[::2], others[1::2])]
+        if k % 5 == 4:
+            decos = decos[:3]
+        for y in ys:
+            for d in decos:
+                xs.append(x), zs.append(back ^ y ^ d)
+    return np.array(xs, dtype=np.uint64), np.array(zs, dtype=np.uint64), rng.normal(size=len(xs))
+
+
+@pytest.mark.parametrize("n,seed", [(13, 0), (16, 1), (20, 2)])
+def test_k2_tiled_plan_hopping_groups(native_lib, n, seed):
+    """Planner self-check on hopping-group term lists: the weights rebuilt from HOP records (ACC table, two pattern
+    tables, rho flips, 32-byte entries) and from their generic fall-backs equal the term list's."""
+    import ctypes as C
+
+    hx, hz, hc = hopping_term_list(n, seed)
+    stats = np.zeros(16, dtype=np.uint64)
+    chk = C.c_double(-2.0)
+    u64p, f64p = C.POINTER(C.c_uint64), C.POINTER(C.c_double)
+    rc = native_lib.qc_k2_plan_stats(n, hx.size, hx.ctypes.data_as(u64p), hz.ctypes.data_as(u64p), hc.ctypes.data_as(f64p),
+                                     stats.ctypes.data_as(u64p), C.byref(chk))  # fmt: skip
+    assert rc == 0
+    n_x, n_tiled, n_pass, n_cubes, n_dot, n_lin, n_left = (int(v) for v in stats[:7])
+    assert n_x == n_tiled == np.unique(hx).size and n_left == 0
+    assert 0.0 <= chk.value < 1e-12
+    assert n_lin > 0 and n_pass < n_x
+
+
 @pytest.mark.parametrize("qubitwise", [True, False])
 def test_native_grouping_equals_numpy_restatement(native_lib, qubitwise):
     """qc_group_commuting (C++/OpenMP) == the numpy restatement of networkx's largest_first greedy colouring, on random
