@@ -734,12 +734,29 @@ double check_host_plan(const HostPlan* plan, size_t T, const uint64_t* xs, const
     for (uint32_t t = 0; t < (uint32_t)kTileSize; ++t) unswz[k2_swizzle(t)] = (uint16_t)t;
     struct CubeGeom {
         uint64_t gen[kRBits];   // generators as index-bit masks
-        int coord[kRBits];      // coordinate bit (index position) of each generator = its lowest bit
+        int piv[kRBits];        // pivot positions (index bits): the tile bits no representative ever sets
+        uint32_t inv[kRBits];   // rows of the inverse of the generators' pivot-bit matrix: element bit j = parity(inv[j] & v)
         int spos[kTileBits];
+        // coordinates (which generators) of the span component of an index, read off its pivot bits
+        uint32_t elem_of(uint64_t idx) const {
+            uint32_t v = 0, e = 0;
+            for (int k = 0; k < kRBits; ++k) v |= (uint32_t)((idx >> piv[k]) & 1ull) << k;
+            for (int j = 0; j < kRBits; ++j) e |= (uint32_t)(popc32(inv[j] & v) & 1) << j;
+            return e;
+        }
     };
-    auto geometry = [&](const TPass& pass, const TRBlock& blk, CubeGeom& cg) {
+    // hdr_unit: the visit's TRBlock (its origin tables follow): the representatives are XOR-combinations of seven tile
+    // bits; the other five are the pivots, on which the five generators must form an invertible matrix
+    auto geometry = [&](const TPass& pass, const TRBlock& blk, uint32_t hdr_unit, CubeGeom& cg) {
         for (int j = 0; j < kTileBits; ++j) cg.spos[j] = pass.spos[j];
-        uint64_t coords = 0;
+        uint32_t origin[24];
+        memcpy(origin, &plan->units[hdr_unit + 2], sizeof(origin));
+        uint32_t free_local = 0;
+        for (uint32_t t = 0; t < 24; ++t) free_local |= origin[t] >> 16;
+        if (free_local >= (uint32_t)kTileSize || popc32(free_local) != kTileBits - kRBits) return false;
+        int np = 0;
+        for (int b = 0; b < kTileBits; ++b)
+            if (!((free_local >> b) & 1u)) cg.piv[np++] = pass.spos[b];
         for (int j = 0; j < kRBits; ++j) {
             if (blk.sbit[j] >= kTileSize) return false;
             const uint32_t local = unswz[blk.sbit[j]];
@@ -747,13 +764,37 @@ double check_host_plan(const HostPlan* plan, size_t T, const uint64_t* xs, const
             cg.gen[j] = 0;
             for (int b = 0; b < kTileBits; ++b)
                 if ((local >> b) & 1u) cg.gen[j] |= 1ull << pass.spos[b];
-            cg.coord[j] = __builtin_ctzll(cg.gen[j]);
-            coords |= 1ull << cg.coord[j];
         }
-        // every generator must carry exactly its own coordinate bit (so that E is read off the coordinate bits)
-        for (int j = 0; j < kRBits; ++j)
-            if ((cg.gen[j] & coords) != (1ull << cg.coord[j])) return false;
-        return popc64(coords) == kRBits;
+        // N[k] = bits (over generators j) of pivot k:  v = N E;  invert by Gauss-Jordan on [N | I]
+        uint32_t rows[kRBits];
+        for (int k = 0; k < kRBits; ++k) {
+            uint32_t r = 0;
+            for (int j = 0; j < kRBits; ++j) r |= (uint32_t)((cg.gen[j] >> cg.piv[k]) & 1ull) << j;
+            rows[k] = r | (1u << (kRBits + k));
+        }
+        for (int col = 0; col < kRBits; ++col) {
+            int pr = -1;
+            for (int k = col; k < kRBits; ++k)
+                if ((rows[k] >> col) & 1u) {
+                    pr = k;
+                    break;
+                }
+            if (pr < 0) return false;  // generators not independent of the representatives
+            std::swap(rows[col], rows[pr]);
+            for (int k = 0; k < kRBits; ++k)
+                if (k != col && ((rows[k] >> col) & 1u)) rows[k] ^= rows[col];
+        }
+        for (int j = 0; j < kRBits; ++j) cg.inv[j] = rows[j] >> kRBits;
+        return true;
+    };
+    // a parity cube's sixth bit: the one bit all five two-bit generators share (-1 for any other cube)
+    auto parity_rho_pos = [](const uint64_t* gen) {
+        uint64_t common = ~0ull;
+        for (int j = 0; j < kRBits; ++j) {
+            if (popc64(gen[j]) != 2) return -1;
+            common &= gen[j];
+        }
+        return popc64(common) == 1 ? (int)__builtin_ctzll(common) : -1;
     };
     // index: x-mask -> record segments (pass, sub-cube visit, first unit, unit count), in execution order
     struct Where {
@@ -768,7 +809,7 @@ double check_host_plan(const HostPlan* plan, size_t T, const uint64_t* xs, const
             const uint32_t hdr_unit = pass.blob_off + rb * kRBlockUnits;
             memcpy(&blk, &plan->units[hdr_unit], sizeof(blk));
             CubeGeom cg;
-            if (!geometry(pass, blk, cg)) return -1.0;
+            if (!geometry(pass, blk, hdr_unit, cg)) return -1.0;
             // the 128 thread representatives x 32 elements must tile the 4096 slots exactly once
             uint32_t origin[24];
             memcpy(origin, &plan->units[hdr_unit + 2], sizeof(origin));
@@ -873,16 +914,11 @@ double check_host_plan(const HostPlan* plan, size_t T, const uint64_t* xs, const
             TRBlock blk;
             memcpy(&blk, &plan->units[w.rblock_unit], sizeof(blk));
             CubeGeom cg;
-            geometry(pass, blk, cg);
-            // coordinate vector of x: read at the coordinate bits (x is in the span, checked when `where` was built)
-            uint32_t xr = 0;
-            for (int j = 0; j < kRBits; ++j) xr |= (uint32_t)((x >> cg.coord[j]) & 1ull) << j;
+            geometry(pass, blk, w.rblock_unit, cg);
+            // coordinate vector of x (x is in the span, checked when `where` was built)
+            const uint32_t xr = cg.elem_of(x);
             uint64_t i = i_raw;
-            auto elem_of = [&](uint64_t idx) {
-                uint32_t e = 0;
-                for (int j = 0; j < kRBits; ++j) e |= (uint32_t)((idx >> cg.coord[j]) & 1ull) << j;
-                return e;
-            };
+            auto elem_of = [&](uint64_t idx) { return cg.elem_of(idx); };
             int k = -1;  // index of the element among the products of a record
             if (xr) {
                 const int hb = 31 - __builtin_clz(xr);
@@ -924,7 +960,7 @@ double check_host_plan(const HostPlan* plan, size_t T, const uint64_t* xs, const
                 }
                 if (kind == kRecDot && meta_mode(h.meta) == kModeHop) {
                     if (k < 0) return -1.0;
-                    const int rho_pos = popc64(cg.gen[0]) == 2 ? 63 - __builtin_clzll(cg.gen[0]) : -1;
+                    const int rho_pos = parity_rho_pos(cg.gen);
                     if (rho_pos < 0) return -1.0;
                     const uint32_t rho = (uint32_t)((c >> rho_pos) & 1ull);
                     double tabs[3][16];
@@ -948,7 +984,7 @@ double check_host_plan(const HostPlan* plan, size_t T, const uint64_t* xs, const
                 memcpy(&r.h, &plan->units[u], sizeof(r.h));
                 {
                     // thread-id bit 6 of a parity cube = the representative's sixth bit (highest bit of the generators)
-                    const int rho_pos = popc64(cg.gen[0]) == 2 ? 63 - __builtin_clzll(cg.gen[0]) : -1;
+                    const int rho_pos = parity_rho_pos(cg.gen);
                     const uint32_t rho = (rho_pos >= 0 && (h.meta & kMetaTwoTables)) ? (uint32_t)((c >> rho_pos) & 1ull) : 0u;
                     memcpy(r.tab, &plan->units[u + 1 + 8 * rho], sizeof(r.tab));
                 }
