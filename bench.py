@@ -320,8 +320,7 @@ def main():
         "hbm_actual_GBps": (hbm_actual * d["launches"] / 1e9 / (d["ms"] / 1e3)) if (hbm_actual and d["ms"]) else None,
         "peak_source": "MEASURED_PEAKS.json hbm_gbs (copy, read+write)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
         # dram__bytes_read.sum + dram__bytes_write.sum per K2T launch from the committed ncu --set full capture of this
-        # command at 30 qubits (profiles/r1_ncu_full_k2t_30q_v5.csv: 17.18 GB read + ~5 MB written per pass; the pass
-        # structure -- one cp.async read of every amplitude -- is unchanged since that capture)
+        # command at 30 qubits (profiles/r1_ncu_full_k2t_30q_v13.csv: 17.18-17.19 GB read + ~5 MB written per pass)
         "traffic": 17.187e9 if (dom == "k2_tiled" and wl["n"] == 30) else None,
         "fp64": fp64,
         "launches": d["launches"], "avg_launch_ms": d["ms"] / max(d["launches"], 1),
