@@ -54,6 +54,7 @@ def parse_args():
     ap.add_argument("--terms", type=int, default=100_000)
     ap.add_argument("--cpu-sample-qubits", type=int, default=24)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity-check", action="store_true", help="N > 1: skip the oracle / 1-GPU-twin parity checks")
     ap.add_argument("--no-full-stream", action="store_true", help="skip the extra full-UCCSD-stream measurement")
     return ap.parse_args()
 
@@ -128,6 +129,7 @@ def cpu_reference_sample(wl_full: dict, sample_qubits: int, budget_s: float = 20
     from qibochem_b200.ansatz.utils import generate_excitations
     from qibochem_b200.pauli import masks_to_string
 
+    OC.set_num_threads(0)  # every logical core: torchrun's OMP_NUM_THREADS=1 must not leak into the baseline
     n_full, ns = wl_full["n"], min(sample_qubits, wl_full["n"])
     nelec_s = max(2, round(wl_full["nelec"] * ns / n_full))
     nelec_s -= nelec_s % 2
@@ -184,7 +186,49 @@ def cpu_reference_sample(wl_full: dict, sample_qubits: int, budget_s: float = 20
             f"{w_full:.1f} passes"
         ),
         "seconds_per_eval_extrapolated": t_eval,
+        # the value is an EXTRAPOLATION of the measured sample, never a measured full-size run
+        "extrapolated": True,
+        "sample_qubits": ns,
+        "scale": scale,
+        "sample_seconds_measured": t_rot + t_term,
+        "host_logical_cores": os.cpu_count(),
     }
+
+
+def cpu_scaling_points(gate_budget_s: float = 12.0) -> dict:
+    """per-gate-pass time of the two CPU restatements at n = 20, 22, 24, 26 (MEASURED), the effective
+    bytes/s they give (one gate pass reads and writes every amplitude: 32 B x 2^n), and the 30-qubit figure they
+    extrapolate to.  "qibojit-equivalent" = in-place C/OpenMP passes on every host core (oracle/oracle_c.c);
+    "qibo-numpy-equivalent" = out-of-place single-threaded numpy passes (oracle/oracle.py, what qibo's default backend
+    does [recalled])."""
+    from oracle import oracle as O
+    from oracle import oracle_c as OC
+
+    threads = OC.set_num_threads(0)
+    rows = []
+    for n in (20, 22, 24, 26):
+        gates = O.expi_pauli_gates(f"X0 Z1 Z2 Y5 X9 Y{n - 1}", 0.1)  # one string of a double: H/S/CNOT ladder/RZ mix
+        st = np.zeros(1 << n, dtype=np.complex128)
+        st[1] = 1.0
+        OC.run_gates(st, n, gates[:2])  # page the buffer in, warm the pool
+        t0 = time.perf_counter()
+        OC.run_gates(st, n, gates)
+        t_c = (time.perf_counter() - t0) / len(gates)
+        row = {"qubits": n, "c_openmp_s_per_pass": t_c, "c_openmp_GBps": 32.0 * 2.0**n / t_c / 1e9}
+        if n <= 24 and gate_budget_s > 0:
+            k = 8 if n <= 22 else 3
+            t0 = time.perf_counter()
+            O.run_gates(n, gates[:k], st)
+            t_np = (time.perf_counter() - t0) / k
+            row.update(numpy_1thread_s_per_pass=t_np, numpy_1thread_GBps=32.0 * 2.0**n / t_np / 1e9)
+        rows.append(row)
+        del st
+    bw_c = float(np.median([r["c_openmp_GBps"] for r in rows[1:]]))  # n >= 22: beyond the last-level cache
+    bw_np = float(np.median([r["numpy_1thread_GBps"] for r in rows if "numpy_1thread_GBps" in r and r["qubits"] >= 22]))
+    return {"measured": rows, "threads": threads,
+            "fitted_GBps": {"c_openmp_all_cores": bw_c, "numpy_single_thread": bw_np},
+            "extrapolated_s_per_pass_30q": {"c_openmp_all_cores": 32.0 * 2.0**30 / bw_c / 1e9, "numpy_single_thread": 32.0 * 2.0**30 / bw_np / 1e9},
+            "note": "measured and extrapolated values are in separate keys; time(30 q evaluation) = gate passes x 32 B x 2^30 / fitted bytes/s"}  # fmt: skip
 
 
 def reference_gates_per_rotation(wl: dict) -> float:
@@ -207,16 +251,21 @@ def run_reference(args, n, nelec, out):
     for _ in range(args.warmup):
         cpu_reference_sample(wl, min(args.cpu_sample_qubits, 22), budget_s=2.0)
     for _ in range(args.steps):
-        last = cpu_reference_sample(wl, args.cpu_sample_qubits, budget_s=12.0)
+        last = cpu_reference_sample(wl, args.cpu_sample_qubits, budget_s=8.0)
         vals.append(last["value"])
     v = float(np.mean(vals)) * float(2 ** (n - 30))
+    extra = {k: last[k] for k in ("extrapolated", "sample_qubits", "scale", "sample_seconds_measured", "host_logical_cores", "seconds_per_eval_extrapolated")}
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": unit_for(n), "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / (v / 2 ** (n - 30)), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64 (complex128)", "data": "synthetic",
         "config": config_dict(wl, args),
-        "cpu_baseline": {**{k: last[k] for k in ("unit", "cores", "kind", "sample")}, "value": v},
+        "cpu_baseline": {**{k: last[k] for k in ("unit", "cores", "kind", "sample")}, "value": v, **extra},
         "e2e": {"value": v, "unit": unit_for(n), "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        # value / ms_per_step are EXTRAPOLATED from a measured sample at `sample_qubits` (x `scale` in 2^n and the gate
+        # census of the full stream); each timed step really ran `sample_seconds_measured` of CPU work
+        "extrapolated": True, "sample_qubits": last["sample_qubits"], "scale": last["scale"],
+        "measured_seconds_per_step": last["sample_seconds_measured"],
     }  # fmt: skip
     out.emit(line)
 
@@ -302,38 +351,14 @@ def main():
     e2e = measure_e2e(wl, args, st)
 
     # ---- roofline of the dominant kernel (by device time inside the timed region)
-    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else None
-    peak = peaks["hbm_gbs"] if peaks else 6650.0
-    dom = max((k for k in prof if prof[k]["launches"]), key=lambda k: prof[k]["ms"])
-    d = prof[dom]
-    achieved = d["bytes"] / 1e9 / (d["ms"] / 1e3) if d["ms"] else 0.0
-    b_n = 16.0 * 2.0 ** wl["n"]
-    # HBM bytes a launch really moves: a tiled K2 pass reads the shard once however many x-masks it serves
-    hbm_actual = {"k2_tiled": b_n, "k2_expectation": None, "k1_rotation": 2 * b_n}.get(dom)
-    fp64 = k2_fp64_roofline(wl, prof, args) if dom == "k2_tiled" else None
-    roofline = {
-        "kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "note": ("achieved = algorithmic bytes (SURVEY 8d: 16*2^n per distinct x-mask) / device time; the tiled kernel "
-                 "serves many x-masks from one HBM read, so this exceeds the HBM peak by design -- hbm_actual_GBps is "
-                 "what crosses the memory bus; the kernel is bound by FP64 issue and shared-memory bandwidth (see fp64)")
-        if dom == "k2_tiled" else "achieved = algorithmic bytes / device time",
-        "hbm_actual_GBps": (hbm_actual * d["launches"] / 1e9 / (d["ms"] / 1e3)) if (hbm_actual and d["ms"]) else None,
-        "peak_source": "MEASURED_PEAKS.json hbm_gbs (copy, read+write)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
-        # dram__bytes_read.sum + dram__bytes_write.sum per K2T launch from the committed ncu --set full capture of this
-        # command at 30 qubits (profiles/r1_ncu_full_k2t_30q_v13.csv: 17.18-17.19 GB read + ~5 MB written per pass)
-        "traffic": 17.187e9 if (dom == "k2_tiled" and wl["n"] == 30) else None,
-        "fp64": fp64,
-        "launches": d["launches"], "avg_launch_ms": d["ms"] / max(d["launches"], 1),
-        "algorithmic_bytes_per_launch": d["bytes"] / max(d["launches"], 1),
-        "share_of_step": d["ms"] / dev_ms,
-        "by_kernel": {k: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps,
-                          "algorithmic_GBps": (v["bytes"] / 1e9 / (v["ms"] / 1e3)) if v["ms"] else None}
-                      for k, v in prof.items() if v["launches"]},
-    }  # fmt: skip
+    roofline = build_roofline(wl, prof, args, dev_ms)
     launches = int(sum(v["launches"] for v in prof.values()))
 
     full = None if (args.no_full_stream or args.rotations != 1024) else measure_full_stream(wl, st, stream)
-    cpu = None if args.no_cpu_baseline else cpu_reference_sample(wl, args.cpu_sample_qubits)
+    cpu = None
+    if not args.no_cpu_baseline:
+        cpu = cpu_reference_sample(wl, args.cpu_sample_qubits)
+        cpu["fit"] = cpu_scaling_points()
     line = {
         "metric": METRIC, "value": value * 2.0 ** (n - 30), "unit": unit_for(n), "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -345,6 +370,66 @@ def main():
         "full_uccsd_stream": full,
     }  # fmt: skip
     out.emit(line)
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    return json.load(open(path)) if os.path.exists(path) else None
+
+
+# FP64 issue peak of a B200 SM: 63.4 DFMA/clk/SM, measured on this pool's B200 by tools/ubench/fp64_pipe.cu
+# (profiles/r1_fp64_pipe_b200.txt).  MEASURED_PEAKS.json carries HBM and bf16 figures only -- it has NO FP64 entry.
+FP64_DFMA_PER_CLK_SM = 63.4
+# dram__bytes_read.sum + dram__bytes_write.sum per K2T launch (30 q): CONSTANT taken from the committed ncu --set full
+# capture of this command, not a live counter of the run that prints it (see "traffic_source")
+K2T_TRAFFIC_30Q = {"bytes": 17.187e9, "source": "ncu --set full capture, profiles/r2_ncu_full_k2t_30q.csv (r1: profiles/r1_ncu_full_k2t_30q_v13.csv): 17.18-17.19 GB read + ~5 MB written per pass"}
+
+
+def build_roofline(wl, prof, args, dev_ms):
+    """Names the resource that binds the dominant kernel.  K2T (tiled expectation): FP64 issue -- one HBM read of the
+    shard serves ~80 x-masks, so the per-x-mask algorithmic bytes of SURVEY 8d are NOT a traffic floor for it; they are
+    kept as `algorithmic_hbm_equiv`.  Every other kernel class: HBM."""
+    peaks = load_peaks()
+    hbm_peak = peaks["hbm_gbs"] if peaks else 6650.0
+    hbm_src = "MEASURED_PEAKS.json hbm_gbs (copy, read+write)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    dom = max((k for k in prof if prof[k]["launches"]), key=lambda k: prof[k]["ms"])
+    d = prof[dom]
+    secs = d["ms"] / 1e3
+    algo_gbps = d["bytes"] / 1e9 / secs if secs else 0.0
+    b_n = 16.0 * 2.0 ** wl["n"]
+    hbm_actual = {"k2_tiled": b_n, "k1_rotation": 2 * b_n}.get(dom)  # bytes a launch really moves
+    hbm_actual_gbps = (hbm_actual * d["launches"] / 1e9 / secs) if (hbm_actual and secs) else None
+    common = {
+        "kernel": dom, "launches": d["launches"], "avg_launch_ms": d["ms"] / max(d["launches"], 1),
+        "share_of_step": d["ms"] / dev_ms,
+        "by_kernel": {k: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps,
+                          "algorithmic_GBps": (v["bytes"] / 1e9 / (v["ms"] / 1e3)) if v["ms"] else None}
+                      for k, v in prof.items() if v["launches"]},
+    }  # fmt: skip
+    fp64 = k2_fp64_roofline(wl, prof, args) if dom == "k2_tiled" else None
+    if fp64 is not None:
+        tf = fp64["achieved"] * 2.0 / 1e12  # DFMA-rate: 2 flop per FP64 instruction
+        tf_peak = fp64["peak"] * 2.0 / 1e12
+        traffic = K2T_TRAFFIC_30Q if wl["n"] == 30 else {"bytes": None, "source": None}
+        return {
+            **common, "bound": "fp64_issue", "achieved": tf, "peak": tf_peak, "unit": "TFLOP/s", "frac": tf / tf_peak,
+            "peak_source": fp64["peak_source"] + "; MEASURED_PEAKS.json has no FP64 entry (HBM and bf16 only)",
+            "note": "FP64 instructions per evaluation counted from the plan (52 per DOT record and thread, 3 per LIN/HOP entry) x 2 flop / "
+                    "device time of the K2T launches, against the measured DFMA issue rate",
+            "traffic": traffic["bytes"], "traffic_source": traffic["source"],
+            "hbm_actual": {"GBps": hbm_actual_gbps, "peak": hbm_peak, "frac": hbm_actual_gbps / hbm_peak if hbm_actual_gbps else None,
+                           "bytes_per_launch": hbm_actual, "peak_source": hbm_src,
+                           "note": "one pass reads the shard once; this is what crosses the memory bus"},
+            "algorithmic_hbm_equiv": {"GBps": algo_gbps, "bytes_per_launch": d["bytes"] / max(d["launches"], 1),
+                                      "note": "SURVEY 8d figure (16 B x 2^n per distinct x-mask) / device time: what one-sweep-per-x-mask "
+                                              "would have to move; exceeds the HBM peak because a tile serves many x-masks -- not a bound"},
+            "fp64": fp64,
+        }  # fmt: skip
+    return {
+        **common, "bound": "hbm", "achieved": algo_gbps, "peak": hbm_peak, "unit": "GB/s", "frac": algo_gbps / hbm_peak,
+        "peak_source": hbm_src, "note": "achieved = algorithmic bytes / device time", "traffic": None,
+        "hbm_actual": {"GBps": hbm_actual_gbps}, "algorithmic_bytes_per_launch": d["bytes"] / max(d["launches"], 1),
+    }  # fmt: skip
 
 
 def measure_full_stream(wl, st, stream):
@@ -390,7 +475,7 @@ def k2_fp64_roofline(wl, prof, args):
     threads = 2.0 ** wl["n"] / 32.0  # one thread per 32-amplitude sub-cube
     fp64_instr = (52.0 * n_dot + 3.0 * n_lin) * threads  # per energy evaluation
     seconds = prof["k2_tiled"]["ms"] / 1e3 / args.steps
-    peak_instr = 63.4 * 148 * 1.965e9
+    peak_instr = FP64_DFMA_PER_CLK_SM * 148 * 1.965e9
     return {"unit": "FP64 instr/s (DFMA-rate)", "achieved": fp64_instr / seconds, "peak": peak_instr, "frac": fp64_instr / seconds / peak_instr,
             "peak_source": "tools/ubench/fp64_pipe.cu on this pool's B200: 63.4 DFMA/clk/SM x 148 SMs x 1.965 GHz (34.9 TFLOP/s)",
             "operand_bound": {"clk_per_record_and_warp": 146.0, "frac": fp64_instr / 52.0 / 32.0 * 146.0 / (seconds * 148 * 4 * 1.965e9),
@@ -411,7 +496,7 @@ def measure_e2e(wl, args, st):
 
     n = wl["n"]
     rt = get_runtime()
-    rt._states[n] = st  # share the already allocated state with the public API's runtime
+    rt.adopt(st)  # share the already allocated state with the public API's runtime
     circuit = Circuit(n)
     circuit.add(gates.X(q) for q in range(wl["nelec"]))
     for x, z, a in zip(wl["rx"].tolist(), wl["rz"].tolist(), wl["ra"].tolist()):
@@ -427,7 +512,7 @@ def measure_e2e(wl, args, st):
         circuit.set_parameters(params[k + 1])
         ham.expectation(circuit)
     dt = (time.perf_counter() - t0) / args.steps
-    rt._states.pop(n, None)
+    rt.forget(st)
     h2d, d2h = (v // args.steps for v in st.transfer_bytes())  # counted by the library at every copy it issues
     return {"value": 2.0 ** (n - 30) / dt, "unit": unit_for(n), "ms_per_step": 1e3 * dt, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
             "note": "the Hamiltonian's tiled plan (3.4 MB) is uploaded once and cached on the device by content hash; per step "

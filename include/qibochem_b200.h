@@ -90,6 +90,16 @@ int qc_k2_plan_stats(int n_local_qubits, size_t T, const uint64_t* xmask, const 
 int qc_energy_gradient(qc_state* h, size_t R, const uint64_t* xmask, const uint64_t* zmask, const double* angle,
                        size_t T, const uint64_t* hxmask, const uint64_t* hzmask, const double* coeff,
                        double* energy_out, double* grad_out);
+/* The three stages of qc_energy_gradient as separate calls, so that a SHARDED run (one process per GPU) can re-layout
+ * psi and lambda between them (x-masks on a global bit need qc_swap_with_peer + qc_swap_scratch_with_peer first):
+ *   qc_hpsi:              lambda (+)= sum_k coeff[k] P_k psi   (lambda = the handle's scratch array; accumulate != 0 adds)
+ *   qc_lambda_inner:      <lambda|psi> over this shard (re = the energy's partial sum)
+ *   qc_gradient_backward: for the given rotations, last to first: grad_out[r] <- this shard's part of dE/d angle[r]
+ *                         = Im<lambda|P_r|psi>, then psi and lambda <- U_r^dagger psi, U_r^dagger lambda. */
+int qc_hpsi(qc_state* h, size_t T, const uint64_t* hxmask, const uint64_t* hzmask, const double* coeff, int accumulate);
+int qc_lambda_inner(qc_state* h, double* re_out, double* im_out);
+int qc_gradient_backward(qc_state* h, size_t R, const uint64_t* xmask, const uint64_t* zmask, const double* angle,
+                         double* grad_out);
 /* <psi|psi> over this shard. */
 int qc_norm2(qc_state* h, double* out);
 
@@ -149,12 +159,17 @@ int qc_copy_state_from_host(qc_state* h, const double* in, uint64_t offset, uint
 /* ---- K4: global <-> local index-bit exchange between two shards over NVLink peer memory -------------------- */
 /* 64-byte CUDA IPC handle of this shard, to be passed to the partner process. */
 int qc_ipc_export(qc_state* h, unsigned char handle[64]);
+/* The same for the scratch array (lambda of the adjoint gradient), allocated on first use; and its device pointer. */
+int qc_ipc_export_scratch(qc_state* h, unsigned char handle[64]);
+int qc_scratch_device_ptr(qc_state* h, void** ptr);
 int qc_ipc_open(qc_state* h, const unsigned char handle[64], void** peer_ptr);
 int qc_ipc_close(qc_state* h, void* peer_ptr);
 /* Swaps the half of this shard where `local_bit` == 1 - my_side with the partner's half where `local_bit` ==
  * my_side ... see DESIGN.md "K4".  Each rank of the pair moves one half of the exchanged elements: `part` in
  * {0,1} selects which. Caller brackets the call with a cross-rank barrier on both sides. */
 int qc_swap_with_peer(qc_state* h, void* peer_ptr, int local_bit, int my_side, int part);
+/* The same exchange on the scratch arrays of the two shards (lambda follows psi through every re-layout). */
+int qc_swap_scratch_with_peer(qc_state* h, void* peer_scratch_ptr, int local_bit, int my_side, int part);
 /* Same exchange inside ONE process between two handles' shards (single-GPU emulation of two ranks for tests, or
  * a single process driving peer-enabled GPUs). */
 int qc_swap_local_pair(qc_state* lo, qc_state* hi, int local_bit);

@@ -327,10 +327,10 @@ def philox4x32(counter: np.ndarray, key: tuple[int, int]) -> np.ndarray:
     return c.astype(np.uint32)
 
 
-def philox_uniform53(nshots: int, seed: int, stream: int = 0) -> np.ndarray:
+def philox_uniform53(nshots: int, seed: int, stream: int = 0, shot_offset: int = 0) -> np.ndarray:
     """One double in [0,1) per shot: counter = (shot_lo, shot_hi, stream, 0), key = (seed_lo, seed_hi);
     u = ((r0 << 21) ^ (r1 >> 11)) * 2^-53 using the first two output words (same recipe as the device sampler)."""
-    idx = np.arange(nshots, dtype=np.uint64)
+    idx = np.arange(nshots, dtype=np.uint64) + np.uint64(shot_offset)
     ctr = np.stack(
         [idx & np.uint64(0xFFFFFFFF), idx >> np.uint64(32), np.full(nshots, stream, np.uint64), np.zeros(nshots, np.uint64)],
         axis=1,

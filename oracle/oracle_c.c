@@ -34,6 +34,16 @@ int oc_num_threads(void) {
 #endif
 }
 
+/* torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU baseline sets its thread count explicitly instead of
+ * inheriting that (0 = all logical cores). */
+void oc_set_num_threads(int n) {
+#ifdef _OPENMP
+    omp_set_num_threads(n > 0 ? n : omp_get_num_procs());
+#else
+    (void)n;
+#endif
+}
+
 static inline uint64_t insert0(uint64_t p, int b) { return ((p >> b) << (b + 1)) | (p & ((1ull << b) - 1)); }
 
 /* one 1-qubit gate pass, in place */
@@ -160,4 +170,24 @@ double oc_expectation_masks(const double* state, int n, int64_t nterms, const ui
         total += coeffs[k] * re;
     }
     return total;
+}
+
+/* per-term values Re<psi|P_k|psi> (the contract of qc_expectation's per_term output) */
+void oc_expectation_masks_per_term(const double* state, int n, int64_t nterms, const uint64_t* xs, const uint64_t* zs,
+                                   double* out) {
+    const cplx* s = (const cplx*)state;
+    const uint64_t dim = 1ull << n;
+    for (int64_t k = 0; k < nterms; ++k) {
+        const uint64_t x = xs[k], z = zs[k];
+        const int ny = __builtin_popcountll(x & z);
+        cplx g = 1;
+        for (int q = 0; q < (ny & 3); ++q) g *= -I;
+        double re = 0.0;
+#pragma omp parallel for schedule(static) reduction(+ : re)
+        for (uint64_t i = 0; i < dim; ++i) {
+            const double sg = (__builtin_popcountll(i & z) & 1) ? -1.0 : 1.0;
+            re += creal(conj(s[i]) * g * sg * s[i ^ x]);
+        }
+        out[k] = re;
+    }
 }

@@ -32,6 +32,12 @@ def num_threads() -> int:
     return load().oc_num_threads()
 
 
+def set_num_threads(n: int = 0) -> int:
+    """Explicit OpenMP thread count (0 = every logical core), independent of an inherited OMP_NUM_THREADS."""
+    load().oc_set_num_threads(C.c_int(int(n)))
+    return num_threads()
+
+
 def encode_gates(gates):
     """oracle gate list [(name, qubits, param)] -> flat arrays"""
     kinds = np.array([KIND[g[0]] for g in gates], dtype=np.int32)
@@ -83,3 +89,14 @@ def expectation_masks(state: np.ndarray, n: int, xs, zs, coeffs) -> float:
         state.ctypes.data_as(C.c_void_p), C.c_int(n), C.c_int64(xs.size), xs.ctypes.data_as(C.c_void_p),
         zs.ctypes.data_as(C.c_void_p), cs.ctypes.data_as(C.c_void_p),
     )  # fmt: skip
+
+
+def expectation_masks_per_term(state: np.ndarray, n: int, xs, zs) -> np.ndarray:
+    xs = np.ascontiguousarray(xs, dtype=np.uint64)
+    zs = np.ascontiguousarray(zs, dtype=np.uint64)
+    out = np.zeros(xs.size, dtype=np.float64)
+    load().oc_expectation_masks_per_term(
+        state.ctypes.data_as(C.c_void_p), C.c_int(n), C.c_int64(xs.size), xs.ctypes.data_as(C.c_void_p),
+        zs.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p),
+    )  # fmt: skip
+    return out

@@ -33,6 +33,9 @@ SIGNATURES = {
     "qc_set_option": (C.c_int, [_vp, C.c_char_p, C.c_int64]),
     "qc_k2_plan_stats": (C.c_int, [C.c_int, C.c_size_t, _u64p, _u64p, _f64p, _u64p, _f64p]),
     "qc_energy_gradient": (C.c_int, [_vp, C.c_size_t, _u64p, _u64p, _f64p, C.c_size_t, _u64p, _u64p, _f64p, _f64p, _f64p]),
+    "qc_hpsi": (C.c_int, [_vp, C.c_size_t, _u64p, _u64p, _f64p, C.c_int]),
+    "qc_lambda_inner": (C.c_int, [_vp, _f64p, _f64p]),
+    "qc_gradient_backward": (C.c_int, [_vp, C.c_size_t, _u64p, _u64p, _f64p, _f64p]),
     "qc_norm2": (C.c_int, [_vp, _f64p]),
     "qc_sample": (C.c_int, [_vp, C.c_uint64, C.c_uint64, C.c_size_t, C.c_uint64, C.c_uint64, _vp, C.c_int, _f64p]),
     "qc_parity_sums": (C.c_int, [_vp, _vp, _vp, C.c_size_t, C.c_int, _u64p, C.c_size_t, _i64p]),
@@ -46,9 +49,12 @@ SIGNATURES = {
     "qc_copy_state_to_host": (C.c_int, [_vp, _f64p, C.c_uint64, C.c_uint64]),
     "qc_copy_state_from_host": (C.c_int, [_vp, _f64p, C.c_uint64, C.c_uint64]),
     "qc_ipc_export": (C.c_int, [_vp, C.c_char_p]),
+    "qc_ipc_export_scratch": (C.c_int, [_vp, C.c_char_p]),
+    "qc_scratch_device_ptr": (C.c_int, [_vp, C.POINTER(_vp)]),
     "qc_ipc_open": (C.c_int, [_vp, C.c_char_p, C.POINTER(_vp)]),
     "qc_ipc_close": (C.c_int, [_vp, _vp]),
     "qc_swap_with_peer": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int]),
+    "qc_swap_scratch_with_peer": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int]),
     "qc_swap_local_pair": (C.c_int, [_vp, _vp, C.c_int]),
 }  # fmt: skip
 

@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libqibochem_b200.so")
-SOURCES = ["state.cu", "rotation.cu", "expectation.cu", "expectation_tiled.cu", "k2_plan.cpp", "gradient.cu", "grouping.cpp", "sampling.cu", "exchange.cu"]
+SOURCES = ["state.cu", "rotation.cu", "expectation.cu", "expectation_tiled.cu", "k2_plan.cpp", "gradient.cu", "gradient_tiled.cu", "grouping.cpp", "sampling.cu", "exchange.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

@@ -24,7 +24,7 @@ from qibochem_b200.runtime import get_runtime
 class Program:
     """Compiled form of a circuit (everything the device needs)."""
 
-    __slots__ = ("nqubits", "basis_index", "xmask", "zmask", "angle", "param_rot", "param_scale", "phase",
+    __slots__ = ("nqubits", "basis_index", "xmask", "zmask", "angle", "param_rot", "param_scale", "param_owner", "phase",
                  "measured", "x_basis_mask", "y_basis_mask")  # fmt: skip
 
 
@@ -33,7 +33,9 @@ class Circuit:
         if kwargs.get("density_matrix"):
             raise NotImplementedError("density-matrix simulation is outside the B200 hot path")
         if kwargs.get("accelerators"):
-            raise NotImplementedError("use qibochem_b200.sharded (one process per GPU) instead of `accelerators`")
+            # qibo's multi-device argument, reached through the reference's **kwargs forwarding (ansatz.py:120, :341):
+            # here one PROCESS per GPU (torchrun); the runtime then shards every state over the ranks
+            get_runtime().configure_accelerators(kwargs["accelerators"])
         self.nqubits = int(nqubits)
         self.init_kwargs = dict(kwargs)
         self.queue: list[_gates.Gate] = []
@@ -110,7 +112,8 @@ class Circuit:
             flat[k] = _gates._real(p)
         if self._program is not None:  # fast path of an optimiser loop: only the angle vector changes
             prog = self._program
-            prog.angle[prog.param_rot] = prog.param_scale * flat
+            # a gate may lower to several rotations that share its parameter (controlled RY, GIVENS, GeneralizedRBS)
+            prog.angle[prog.param_rot] = prog.param_scale * flat[prog.param_owner]
 
     # ---- compilation ------------------------------------------------------------------------------------------
     def program(self) -> Program:
@@ -119,7 +122,8 @@ class Circuit:
         n = self.nqubits
         prog = Program()
         prog.nqubits = n
-        xs, zs, angles, prot, pscale = [], [], [], [], []
+        xs, zs, angles, prot, pscale, powner = [], [], [], [], [], []
+        n_param_gates = 0
         phase = 1.0 + 0.0j
         basis_qubits = 0  # qubit-position mask of leading X gates (they only move the initial basis state: K0)
         leading = True
@@ -143,20 +147,23 @@ class Circuit:
                 if pidx is not None:
                     prot.append(len(xs))
                     pscale.append(scale)
+                    powner.append(n_param_gates)
                 xs.append(reverse_bits(x, n))
                 zs.append(reverse_bits(z, n))
                 angles.append(ang)
+            if g.n_params:
+                n_param_gates += 1
         prog.basis_index = reverse_bits(basis_qubits, n)
         prog.xmask = np.array(xs, dtype=np.uint64)
         prog.zmask = np.array(zs, dtype=np.uint64)
         prog.angle = np.array(angles, dtype=np.float64)
         prog.param_rot = np.array(prot, dtype=np.int64)
         prog.param_scale = np.array(pscale, dtype=np.float64)
+        prog.param_owner = np.array(powner, dtype=np.int64)  # index into parametrized_gates / get_parameters()
         prog.phase = phase
         prog.measured = measured
         prog.x_basis_mask = sum(1 << (n - 1 - q) for q, b in measured if b == "X")
         prog.y_basis_mask = sum(1 << (n - 1 - q) for q, b in measured if b == "Y")
-        # leading X gates are not parametrized, so parametrized gates <-> prog.param_rot are aligned
         self._program = prog
         return prog
 
@@ -208,7 +215,14 @@ def _next_seed() -> int:
     import os
 
     _seed_counter[0] = (_seed_counter[0] * 6364136223846793005 + 1442695040888963407) % (1 << 64)
-    return _seed_counter[0] ^ int.from_bytes(os.urandom(8), "little")
+    seed = _seed_counter[0] ^ int.from_bytes(os.urandom(8), "little")
+    if get_runtime().world > 1:  # every rank of a sharded run must draw from the SAME key: rank 0's
+        import torch.distributed as dist
+
+        box = [seed]
+        dist.broadcast_object_list(box, src=0)
+        seed = int(box[0])
+    return seed
 
 
 class CircuitResult:

@@ -59,6 +59,24 @@ int qc_ipc_export(qc_state* h, unsigned char handle[64]) {
     return 0;
 }
 
+int qc_ipc_export_scratch(qc_state* h, unsigned char handle[64]) {
+    QC_REQUIRE(h && handle, "qc_ipc_export_scratch: null argument");
+    QC_CHECK(cudaSetDevice(h->device));
+    if (!h->scratch_psi) QC_CHECK(cudaMalloc(&h->scratch_psi, h->dim * sizeof(double2)));
+    cudaIpcMemHandle_t hd;
+    QC_CHECK(cudaIpcGetMemHandle(&hd, h->scratch_psi));
+    memcpy(handle, &hd, 64);
+    return 0;
+}
+
+int qc_scratch_device_ptr(qc_state* h, void** ptr) {
+    QC_REQUIRE(h && ptr, "qc_scratch_device_ptr: null argument");
+    QC_CHECK(cudaSetDevice(h->device));
+    if (!h->scratch_psi) QC_CHECK(cudaMalloc(&h->scratch_psi, h->dim * sizeof(double2)));
+    *ptr = h->scratch_psi;
+    return 0;
+}
+
 int qc_ipc_open(qc_state* h, const unsigned char handle[64], void** peer_ptr) {
     QC_REQUIRE(h && handle && peer_ptr, "qc_ipc_open: null argument");
     QC_CHECK(cudaSetDevice(h->device));
@@ -76,9 +94,21 @@ int qc_ipc_close(qc_state* h, void* peer_ptr) {
     return 0;
 }
 
+static int swap_array_with_peer(qc_state* h, double2* mine, void* peer_ptr, int local_bit, int my_side, int part);
+
 int qc_swap_with_peer(qc_state* h, void* peer_ptr, int local_bit, int my_side, int part) {
-    using namespace qc;
     QC_REQUIRE(h && peer_ptr, "qc_swap_with_peer: null argument");
+    return swap_array_with_peer(h, h->psi, peer_ptr, local_bit, my_side, part);
+}
+
+int qc_swap_scratch_with_peer(qc_state* h, void* peer_scratch_ptr, int local_bit, int my_side, int part) {
+    QC_REQUIRE(h && peer_scratch_ptr, "qc_swap_scratch_with_peer: null argument");
+    QC_REQUIRE(h->scratch_psi, "qc_swap_scratch_with_peer: this shard has no scratch array yet");
+    return swap_array_with_peer(h, h->scratch_psi, peer_scratch_ptr, local_bit, my_side, part);
+}
+
+static int swap_array_with_peer(qc_state* h, double2* mine, void* peer_ptr, int local_bit, int my_side, int part) {
+    using namespace qc;
     QC_REQUIRE(local_bit >= 0 && local_bit < h->n, "qc_swap_with_peer: local_bit out of range");
     QC_REQUIRE((my_side == 0 || my_side == 1) && (part == 0 || part == 1), "qc_swap_with_peer: side/part must be 0 or 1");
     QC_CHECK(cudaSetDevice(h->device));
@@ -87,8 +117,8 @@ int qc_swap_with_peer(qc_state* h, void* peer_ptr, int local_bit, int my_side, i
     const uint64_t p_begin = part == 0 ? 0 : (half ? half : npairs);
     const uint64_t p_end = part == 0 ? (half ? half : npairs) : npairs;
     if (p_begin >= p_end) return 0;
-    double2* a = my_side == 0 ? h->psi : (double2*)peer_ptr;
-    double2* b = my_side == 0 ? (double2*)peer_ptr : h->psi;
+    double2* a = my_side == 0 ? mine : (double2*)peer_ptr;
+    double2* b = my_side == 0 ? (double2*)peer_ptr : mine;
     const int nb = grid_for(p_end - p_begin, 4, h->sm_count);
     LaunchScope ls(h, kK4Exchange, 32.0 * (double)(p_end - p_begin));
     swap_bit_kernel<4><<<nb, kThreads, 0, h->stream>>>(a, b, p_begin, p_end, local_bit);

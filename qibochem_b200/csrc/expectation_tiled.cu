@@ -33,6 +33,14 @@ struct TiledPlan {
     uint64_t hash = 0;
     HostPlan* host = nullptr;
     uint4* d_units = nullptr;
+    // the term list the plan was built from: the plan bakes the coefficients in, so a cache hit needs the lists to be
+    // IDENTICAL, not merely to hash alike (H and -H must never share a plan)
+    std::vector<uint64_t> key_x, key_z;
+    std::vector<double> key_c;
+    bool matches(size_t T, const uint64_t* xs, const uint64_t* zs, const double* cs) const {
+        return key_x.size() == T && memcmp(key_x.data(), xs, T * 8) == 0 && memcmp(key_z.data(), zs, T * 8) == 0 &&
+               memcmp(key_c.data(), cs, T * 8) == 0;
+    }
 };
 
 void free_tiled_plan(TiledPlan* p) {
@@ -382,12 +390,16 @@ __global__ void __launch_bounds__(kTileThreads, 2)
 // ---------------------------------------------------------------------------------------------------------------
 // host
 // ---------------------------------------------------------------------------------------------------------------
-static uint64_t fnv1a(const void* data, size_t bytes, uint64_t h) {
+// word-wise hash with a full finalizer per word (splitmix64), so that high input bits -- the sign and exponent of a
+// coefficient -- diffuse into every bit of the hash; a hit is confirmed by comparing the term lists themselves
+static uint64_t hash_words(const void* data, size_t bytes, uint64_t h) {
     const uint64_t* w = (const uint64_t*)data;
     const size_t nw = bytes / 8;
     for (size_t i = 0; i < nw; ++i) {
-        h ^= w[i];
-        h *= 0x100000001b3ull;
+        uint64_t v = w[i] + 0x9e3779b97f4a7c15ull + h;
+        v = (v ^ (v >> 30)) * 0xbf58476d1ce4e5b9ull;
+        v = (v ^ (v >> 27)) * 0x94d049bb133111ebull;
+        h = (h << 7 | h >> 57) ^ v ^ (v >> 31);
     }
     return h;
 }
@@ -410,13 +422,13 @@ static TiledPlan* upload_plan(HostPlan* hp, uint64_t hash) {
 int run_tiled_expectation(qc_state* h, size_t T, const uint64_t* xs, const uint64_t* zs, const double* cs, int out_slot,
                           int* n_passes_out, const TiledPlan** plan_out) {
     uint64_t hash = 0xcbf29ce484222325ull ^ (uint64_t)T ^ ((uint64_t)h->n << 56);
-    hash = fnv1a(xs, T * 8, hash);
-    hash = fnv1a(zs, T * 8, hash);
-    hash = fnv1a(cs, T * 8, hash);
+    hash = hash_words(xs, T * 8, hash);
+    hash = hash_words(zs, T * 8, hash);
+    hash = hash_words(cs, T * 8, hash);
     constexpr size_t kMaxCachedPlans = 8;  // a sharded energy walks through a few layouts, each with its own term list
     TiledPlan* found = nullptr;
     for (size_t i = 0; i < h->k2plans.size(); ++i)
-        if (h->k2plans[i]->hash == hash && h->k2plans[i]->host->n == h->n) {
+        if (h->k2plans[i]->hash == hash && h->k2plans[i]->host->n == h->n && h->k2plans[i]->matches(T, xs, zs, cs)) {
             found = h->k2plans[i];
             h->k2plans.erase(h->k2plans.begin() + i);
             break;
@@ -426,6 +438,9 @@ int run_tiled_expectation(qc_state* h, size_t T, const uint64_t* xs, const uint6
         QC_REQUIRE(hp != nullptr, "qc_expectation: could not build the tiled plan");
         found = upload_plan(hp, hash);
         QC_REQUIRE(found != nullptr, "qc_expectation: could not upload the tiled plan");
+        found->key_x.assign(xs, xs + T);
+        found->key_z.assign(zs, zs + T);
+        found->key_c.assign(cs, cs + T);
         h->h2d_bytes += hp->units.size() * sizeof(Unit16);
         if (h->k2plans.size() >= kMaxCachedPlans) {
             QC_CHECK(cudaStreamSynchronize(h->stream));  // the evicted plan may still be read by in-flight passes

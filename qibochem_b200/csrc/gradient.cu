@@ -125,26 +125,12 @@ __global__ void __launch_bounds__(kThreads) grad_inner_kernel(const double2* __r
 
 }  // namespace qc
 
-extern "C" int qc_energy_gradient(qc_state* h, size_t R, const uint64_t* rx, const uint64_t* rz, const double* angle,
-                                  size_t T, const uint64_t* hx, const uint64_t* hz, const double* hc,
-                                  double* energy_out, double* grad_out) {
-    using namespace qc;
-    QC_REQUIRE(h && energy_out, "qc_energy_gradient: null argument");
-    QC_REQUIRE(R == 0 || (rx && rz && angle && grad_out), "qc_energy_gradient: null rotation array");
-    QC_REQUIRE(T == 0 || (hx && hz && hc), "qc_energy_gradient: null term array");
-    QC_REQUIRE(T < (1ull << 31), "qc_energy_gradient: too many terms");
-    for (size_t r = 0; r < R; ++r)
-        QC_REQUIRE(rx[r] < h->dim && rz[r] < h->dim, "qc_energy_gradient: rotation mask has bits outside the shard");
-    for (size_t k = 0; k < T; ++k)
-        QC_REQUIRE(hx[k] < h->dim && hz[k] < h->dim, "qc_energy_gradient: term mask has bits outside the shard");
-    QC_CHECK(cudaSetDevice(h->device));
-    *energy_out = 0.0;
-    for (size_t r = 0; r < R; ++r) grad_out[r] = 0.0;
-    if (T == 0) return 0;
-    if (!h->scratch_psi) QC_CHECK(cudaMalloc(&h->scratch_psi, h->dim * sizeof(double2)));
-    double2* lam = h->scratch_psi;
+namespace qc {
 
-    // ---- lambda = H psi: x-groups, Re-type (even nY) terms first
+// lambda (+)= sum_k c_k P_k psi over the given terms (all x-masks local to the shard); lambda = h->scratch_psi.
+int hpsi_sweeps(qc_state* h, size_t T, const uint64_t* hx, const uint64_t* hz, const double* hc, bool accumulate) {
+    double2* lam = h->scratch_psi;
+    // x-groups, Re-type (even nY) terms first
     std::vector<uint32_t> order(T);
     std::iota(order.begin(), order.end(), 0u);
     std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
@@ -177,65 +163,119 @@ extern "C" int qc_energy_gradient(qc_state* h, size_t R, const uint64_t* rx, con
     HGroup* d_groups = nullptr;
     HTerm* d_terms = nullptr;
     QC_CHECK(cudaMalloc(&d_groups, groups.size() * sizeof(HGroup)));
-    QC_CHECK(cudaMalloc(&d_terms, terms.size() * sizeof(HTerm)));
+    if (cudaMalloc(&d_terms, terms.size() * sizeof(HTerm)) != cudaSuccess) {
+        cudaFree(d_groups);
+        set_error("hpsi: cudaMalloc failed");
+        return 1;
+    }
     auto cleanup = [&]() {
+        cudaStreamSynchronize(h->stream);
         cudaFree(d_groups);
         cudaFree(d_terms);
     };
     const int nb = grid_for(h->dim, 2, h->sm_count);
-    {
-        size_t g0 = 0;
-        bool first_launch = true;
-        std::vector<HGroup> launch_groups;
-        while (g0 < groups.size()) {
-            size_t g1 = g0;
-            uint32_t nt = 0;
-            launch_groups.clear();
-            while (g1 < groups.size() && g1 - g0 < (size_t)kHGroupsPerLaunch && nt + groups[g1].n_re + groups[g1].n_im <= (uint32_t)kHTermsPerLaunch) {
-                HGroup g = groups[g1];
-                g.first -= groups[g0].first;  // relative to the launch's first term
-                launch_groups.push_back(g);
-                nt += groups[g1].n_re + groups[g1].n_im;
-                ++g1;
-            }
-            if (cudaMemcpyAsync(d_groups + g0, launch_groups.data(), launch_groups.size() * sizeof(HGroup), cudaMemcpyHostToDevice, h->stream) != cudaSuccess ||
-                cudaMemcpyAsync(d_terms + groups[g0].first, terms.data() + groups[g0].first, nt * sizeof(HTerm), cudaMemcpyHostToDevice, h->stream) != cudaSuccess) {
-                cleanup();
-                set_error("qc_energy_gradient: upload failed");
-                return 1;
-            }
-            h->h2d_bytes += launch_groups.size() * sizeof(HGroup) + nt * sizeof(HTerm);
-            // pageable host memory: the async copies above are staged synchronously, so the vectors may be reused
-            {
-                LaunchScope ls(h, kGradient, 16.0 * (double)h->dim * (double)(launch_groups.size() + 2));
-                hpsi_kernel<<<nb, kThreads, 0, h->stream>>>(h->psi, lam, h->dim, d_groups + g0, (int)launch_groups.size(),
-                                                            d_terms + groups[g0].first, (int)nt, first_launch ? 0 : 1);
-            }
-            first_launch = false;
-            g0 = g1;
+    size_t g0 = 0;
+    bool first_launch = !accumulate;
+    std::vector<HGroup> launch_groups;
+    while (g0 < groups.size()) {
+        size_t g1 = g0;
+        uint32_t nt = 0;
+        launch_groups.clear();
+        while (g1 < groups.size() && g1 - g0 < (size_t)kHGroupsPerLaunch && nt + groups[g1].n_re + groups[g1].n_im <= (uint32_t)kHTermsPerLaunch) {
+            HGroup g = groups[g1];
+            g.first -= groups[g0].first;  // relative to the launch's first term
+            launch_groups.push_back(g);
+            nt += groups[g1].n_re + groups[g1].n_im;
+            ++g1;
         }
+        if (cudaMemcpyAsync(d_groups + g0, launch_groups.data(), launch_groups.size() * sizeof(HGroup), cudaMemcpyHostToDevice, h->stream) != cudaSuccess ||
+            cudaMemcpyAsync(d_terms + groups[g0].first, terms.data() + groups[g0].first, nt * sizeof(HTerm), cudaMemcpyHostToDevice, h->stream) != cudaSuccess) {
+            cleanup();
+            set_error("hpsi: upload failed");
+            return 1;
+        }
+        h->h2d_bytes += launch_groups.size() * sizeof(HGroup) + nt * sizeof(HTerm);
+        // pageable host memory: the async copies above are staged synchronously, so the vectors may be reused
+        {
+            LaunchScope ls(h, kGradient, 16.0 * (double)h->dim * (double)(launch_groups.size() + 2));
+            hpsi_kernel<<<nb, kThreads, 0, h->stream>>>(h->psi, lam, h->dim, d_groups + g0, (int)launch_groups.size(),
+                                                        d_terms + groups[g0].first, (int)nt, first_launch ? 0 : 1);
+        }
+        first_launch = false;
+        g0 = g1;
     }
-    if (cudaGetLastError() != cudaSuccess) {
-        cleanup();
-        set_error("qc_energy_gradient: hpsi launch failed");
+    const cudaError_t e = cudaGetLastError();
+    cleanup();
+    if (e != cudaSuccess) {
+        set_error(std::string("hpsi launch failed: ") + cudaGetErrorString(e));
         return 1;
     }
+    return 0;
+}
 
-    // ---- E = Re <psi|lambda>  (slot 0/1 of d_out), gradient sums C_j in d_out[2 + 2 r ...]
-    if (h->ensure_partials((size_t)nb * 2 * kGradStrings) || h->ensure_out(2 + 2 * R + 2 * kGradStrings)) {
-        cleanup();
-        return 1;
+int hpsi_tiled(qc_state* h, size_t T, const uint64_t* hx, const uint64_t* hz, const double* hc, bool accumulate,
+               bool* handled);  // gradient_tiled.cu
+
+static int ensure_lambda(qc_state* h) {
+    if (!h->scratch_psi) QC_CHECK(cudaMalloc(&h->scratch_psi, h->dim * sizeof(double2)));
+    return 0;
+}
+
+}  // namespace qc
+
+extern "C" int qc_hpsi(qc_state* h, size_t T, const uint64_t* hx, const uint64_t* hz, const double* hc, int accumulate) {
+    using namespace qc;
+    QC_REQUIRE(h, "qc_hpsi: null handle");
+    QC_REQUIRE(T == 0 || (hx && hz && hc), "qc_hpsi: null term array");
+    QC_REQUIRE(T < (1ull << 31), "qc_hpsi: too many terms");
+    for (size_t k = 0; k < T; ++k)
+        QC_REQUIRE(hx[k] < h->dim && hz[k] < h->dim, "qc_hpsi: term mask has bits outside the shard");
+    QC_CHECK(cudaSetDevice(h->device));
+    if (ensure_lambda(h)) return 1;
+    if (T == 0) {
+        if (!accumulate) QC_CHECK(cudaMemsetAsync(h->scratch_psi, 0, h->dim * sizeof(double2), h->stream));
+        return 0;
     }
+    bool handled = false;
+    if (hpsi_tiled(h, T, hx, hz, hc, accumulate != 0, &handled)) return 1;
+    if (handled) return 0;
+    return hpsi_sweeps(h, T, hx, hz, hc, accumulate != 0);
+}
+
+extern "C" int qc_lambda_inner(qc_state* h, double* re_out, double* im_out) {
+    using namespace qc;
+    QC_REQUIRE(h && re_out && im_out, "qc_lambda_inner: null argument");
+    QC_REQUIRE(h->scratch_psi, "qc_lambda_inner: no lambda (call qc_hpsi first)");
+    QC_CHECK(cudaSetDevice(h->device));
+    const int nb = grid_for(h->dim, 2, h->sm_count);
+    if (h->ensure_partials((size_t)nb * 2) || h->ensure_out(2)) return 1;
     {
         LaunchScope ls(h, kGradient, 32.0 * (double)h->dim);
-        inner_kernel<<<nb, kThreads, 0, h->stream>>>(lam, h->psi, h->dim, h->d_partials);
+        inner_kernel<<<nb, kThreads, 0, h->stream>>>(h->scratch_psi, h->psi, h->dim, h->d_partials);
     }
-    if (fold_partials(h, h->d_partials, 2, nb, nb, h->d_out)) {
-        cleanup();
-        return 1;
-    }
+    QC_CHECK(cudaGetLastError());
+    if (fold_partials(h, h->d_partials, 2, nb, nb, h->d_out)) return 1;
+    QC_CHECK(cudaMemcpyAsync(h->h_out, h->d_out, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    h->d2h_bytes += 2 * sizeof(double);
+    QC_CHECK(cudaStreamSynchronize(h->stream));
+    *re_out = h->h_out[0];
+    *im_out = h->h_out[1];
+    return 0;
+}
 
-    // ---- backward over the fused runs
+extern "C" int qc_gradient_backward(qc_state* h, size_t R, const uint64_t* rx, const uint64_t* rz, const double* angle,
+                                    double* grad_out) {
+    using namespace qc;
+    QC_REQUIRE(h, "qc_gradient_backward: null handle");
+    if (R == 0) return 0;
+    QC_REQUIRE(rx && rz && angle && grad_out, "qc_gradient_backward: null rotation array");
+    QC_REQUIRE(h->scratch_psi, "qc_gradient_backward: no lambda (call qc_hpsi first)");
+    for (size_t r = 0; r < R; ++r)
+        QC_REQUIRE(rx[r] < h->dim && rz[r] < h->dim, "qc_gradient_backward: rotation mask has bits outside the shard");
+    QC_CHECK(cudaSetDevice(h->device));
+    double2* lam = h->scratch_psi;
+    const int nb = grid_for(h->dim, 2, h->sm_count);
+    if (h->ensure_partials((size_t)nb * 2 * kGradStrings) || h->ensure_out(2 * R + 2 * kGradStrings)) return 1;
     std::vector<std::pair<size_t, size_t>> runs;
     plan_rotation_runs(R, rx, rz, runs);
     std::vector<double> neg(R);
@@ -252,29 +292,19 @@ extern "C" int qc_energy_gradient(qc_state* h, size_t R, const uint64_t* rx, con
                 LaunchScope ls(h, kGradient, 32.0 * (double)h->dim);
                 grad_inner_kernel<<<nb, kThreads, 0, h->stream>>>(lam, h->psi, h->dim, gr, h->d_partials);
             }
-            if (fold_partials(h, h->d_partials, 2 * gr.count, nb, nb, h->d_out + 2 + 2 * (first + c0))) {
-                cleanup();
-                return 1;
-            }
+            QC_CHECK(cudaGetLastError());
+            if (fold_partials(h, h->d_partials, 2 * gr.count, nb, nb, h->d_out + 2 * (first + c0))) return 1;
         }
         if (apply_rotations_to(h, h->psi, count, rx + first, rz + first, neg.data() + first, 1, nullptr) ||
-            apply_rotations_to(h, lam, count, rx + first, rz + first, neg.data() + first, 1, nullptr)) {
-            cleanup();
+            apply_rotations_to(h, lam, count, rx + first, rz + first, neg.data() + first, 1, nullptr))
             return 1;
-        }
     }
-    h->d2h_bytes += (2 + 2 * R) * sizeof(double);
-    cudaError_t e = cudaMemcpyAsync(h->h_out, h->d_out, (2 + 2 * R) * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-    cleanup();
-    if (e != cudaSuccess) {
-        set_error(std::string("qc_energy_gradient: ") + cudaGetErrorString(e));
-        return 1;
-    }
-    *energy_out = h->h_out[0];
+    h->d2h_bytes += 2 * R * sizeof(double);
+    QC_CHECK(cudaMemcpyAsync(h->h_out, h->d_out, 2 * R * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    QC_CHECK(cudaStreamSynchronize(h->stream));
     for (size_t r = 0; r < R; ++r) {
         // dE/dphi_r = Im[(-i)^{nY} C_r]
-        const double cr = h->h_out[2 + 2 * r], ci = h->h_out[2 + 2 * r + 1];
+        const double cr = h->h_out[2 * r], ci = h->h_out[2 * r + 1];
         switch (__builtin_popcountll(rx[r] & rz[r]) & 3) {
             case 0: grad_out[r] = ci; break;
             case 1: grad_out[r] = -cr; break;
@@ -283,4 +313,20 @@ extern "C" int qc_energy_gradient(qc_state* h, size_t R, const uint64_t* rx, con
         }
     }
     return 0;
+}
+
+extern "C" int qc_energy_gradient(qc_state* h, size_t R, const uint64_t* rx, const uint64_t* rz, const double* angle,
+                                  size_t T, const uint64_t* hx, const uint64_t* hz, const double* hc,
+                                  double* energy_out, double* grad_out) {
+    using namespace qc;
+    QC_REQUIRE(h && energy_out, "qc_energy_gradient: null argument");
+    QC_REQUIRE(R == 0 || (rx && rz && angle && grad_out), "qc_energy_gradient: null rotation array");
+    QC_REQUIRE(T == 0 || (hx && hz && hc), "qc_energy_gradient: null term array");
+    *energy_out = 0.0;
+    for (size_t r = 0; r < R; ++r) grad_out[r] = 0.0;
+    if (T == 0) return 0;
+    double im = 0.0;
+    if (qc_hpsi(h, T, hx, hz, hc, 0)) return 1;
+    if (qc_lambda_inner(h, energy_out, &im)) return 1;
+    return qc_gradient_backward(h, R, rx, rz, angle, grad_out);
 }

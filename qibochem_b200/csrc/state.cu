@@ -97,14 +97,22 @@ int qc_state::ensure_partials(size_t doubles) {
 }
 int qc_state::ensure_out(size_t doubles) {
     if (doubles <= out_cap) return 0;
-    if (d_out) cudaFree(d_out);
-    if (h_out) cudaFreeHost(h_out);
-    d_out = h_out = nullptr;
-    out_cap = 0;
     size_t ncap = 1024;
     while (ncap < doubles) ncap *= 2;
-    QC_CHECK(cudaMalloc(&d_out, ncap * sizeof(double)));
-    QC_CHECK(cudaMallocHost(&h_out, ncap * sizeof(double)));
+    double *nd = nullptr, *nh = nullptr;
+    QC_CHECK(cudaMalloc(&nd, ncap * sizeof(double)));
+    QC_CHECK(cudaMallocHost(&nh, ncap * sizeof(double)));
+    if (d_out) {
+        // growth keeps what earlier launches of the same call already left in the buffer (the tiled sum in slot 0
+        // while the leftover sweeps ask for more slots)
+        QC_CHECK(cudaStreamSynchronize(stream));
+        QC_CHECK(cudaMemcpy(nd, d_out, out_cap * sizeof(double), cudaMemcpyDeviceToDevice));
+        memcpy(nh, h_out, out_cap * sizeof(double));
+        cudaFree(d_out);
+        cudaFreeHost(h_out);
+    }
+    d_out = nd;
+    h_out = nh;
     out_cap = ncap;
     return 0;
 }

@@ -52,22 +52,5 @@ def adjoint_gradient(circuit, hamiltonian, initial_state=None):
     grad = np.zeros(len(circuit.parametrized_gates), dtype=np.float64)
     # a parametrized gate may lower to several rotations that share its parameter: chain rule angle = scale * param
     if prog.param_rot.size:
-        owners = _parameter_owner(circuit, prog)
-        np.add.at(grad, owners, prog.param_scale * g_rot[prog.param_rot])
+        np.add.at(grad, prog.param_owner, prog.param_scale * g_rot[prog.param_rot])
     return float(e + hamiltonian.constant), grad
-
-
-def _parameter_owner(circuit, prog) -> np.ndarray:
-    """For every entry of ``prog.param_rot``: the index of the parametrized gate it belongs to."""
-    owners = []
-    k = 0
-    for g in circuit.queue:
-        if isinstance(g, _gates.M) or not g.n_params:
-            continue
-        rots, _ = g.lower()
-        owners.extend([k] * sum(1 for r in rots if r[3] is not None))
-        k += 1
-    owners = np.array(owners, dtype=np.int64)
-    if owners.size != prog.param_rot.size:
-        raise RuntimeError("internal error: parameter map and program disagree")
-    return owners

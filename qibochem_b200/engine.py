@@ -134,6 +134,35 @@ class DeviceState:
         )  # fmt: skip
         return e.value, grad
 
+    def hpsi(self, hxmask, hzmask, coeff, accumulate: bool = False) -> None:
+        """lambda (+)= sum_k c_k P_k psi into the handle's scratch array (first stage of the adjoint gradient)."""
+        hx, hz, hc = _u64(hxmask), _u64(hzmask), _f64(coeff)
+        if not (hx.shape == hz.shape == hc.shape and hx.ndim == 1):
+            raise ValueError("xmask, zmask and coeff must be 1-d arrays of equal length")
+        _native.check(
+            self._lib.qc_hpsi(self._h, hx.size, _ptr(hx, C.c_uint64), _ptr(hz, C.c_uint64), _ptr(hc, C.c_double), int(bool(accumulate))),
+            "qc_hpsi",
+        )
+
+    def lambda_inner(self) -> complex:
+        """<lambda|psi> over this shard."""
+        re, im = C.c_double(0.0), C.c_double(0.0)
+        _native.check(self._lib.qc_lambda_inner(self._h, C.byref(re), C.byref(im)), "qc_lambda_inner")
+        return complex(re.value, im.value)
+
+    def gradient_backward(self, rxmask, rzmask, angle) -> np.ndarray:
+        """This shard's part of dE/d angle[r] for the given rotations (walked last to first); psi and lambda are left
+        with the rotations un-applied."""
+        rx, rz, ra = _u64(rxmask), _u64(rzmask), _f64(angle)
+        if not (rx.shape == rz.shape == ra.shape and rx.ndim == 1):
+            raise ValueError("xmask, zmask and angle must be 1-d arrays of equal length")
+        grad = np.zeros(rx.size, dtype=np.float64)
+        _native.check(
+            self._lib.qc_gradient_backward(self._h, rx.size, _ptr(rx, C.c_uint64), _ptr(rz, C.c_uint64), _ptr(ra, C.c_double), _ptr(grad, C.c_double)),
+            "qc_gradient_backward",
+        )
+        return grad
+
     def norm2(self) -> float:
         v = C.c_double(0.0)
         _native.check(self._lib.qc_norm2(self._h, C.byref(v)), "qc_norm2")
@@ -277,6 +306,17 @@ class DeviceState:
         _native.check(self._lib.qc_ipc_export(self._h, buf), "qc_ipc_export")
         return buf.raw
 
+    def ipc_export_scratch(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        _native.check(self._lib.qc_ipc_export_scratch(self._h, buf), "qc_ipc_export_scratch")
+        return buf.raw
+
+    @property
+    def scratch_device_ptr(self) -> int:
+        p = C.c_void_p()
+        _native.check(self._lib.qc_scratch_device_ptr(self._h, C.byref(p)), "qc_scratch_device_ptr")
+        return p.value
+
     def ipc_open(self, handle: bytes) -> int:
         p = C.c_void_p()
         _native.check(self._lib.qc_ipc_open(self._h, C.create_string_buffer(handle, 64), C.byref(p)), "qc_ipc_open")
@@ -290,6 +330,13 @@ class DeviceState:
         _native.check(
             self._lib.qc_swap_with_peer(self._h, C.c_void_p(peer_ptr), int(local_bit), int(my_side), int(part)),
             "qc_swap_with_peer",
+        )
+
+    def swap_scratch_with_peer(self, peer_scratch_ptr: int, local_bit: int, my_side: int, part: int | None = None) -> None:
+        part = my_side if part is None else part
+        _native.check(
+            self._lib.qc_swap_scratch_with_peer(self._h, C.c_void_p(peer_scratch_ptr), int(local_bit), int(my_side), int(part)),
+            "qc_swap_scratch_with_peer",
         )
 
     def swap_local_pair(self, other: "DeviceState", local_bit: int) -> None:

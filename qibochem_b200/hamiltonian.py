@@ -130,6 +130,7 @@ class SymbolicHamiltonian:
         from qibochem_b200.circuit import Circuit, CircuitResult
         from qibochem_b200.engine import DeviceState
         from qibochem_b200.runtime import get_runtime
+        from qibochem_b200.sharded import ShardedState
 
         if nshots is not None:
             from qibochem_b200.measurement.result import expectation_from_samples
@@ -142,7 +143,7 @@ class SymbolicHamiltonian:
         elif isinstance(circuit_or_state, CircuitResult):
             circuit_or_state._check_alive()
             st = circuit_or_state._state
-        elif isinstance(circuit_or_state, DeviceState):
+        elif isinstance(circuit_or_state, (DeviceState, ShardedState)):
             st = circuit_or_state
         else:
             psi = np.asarray(circuit_or_state, dtype=np.complex128).reshape(-1)

@@ -41,7 +41,7 @@ def _z_terms_from_frequencies(keys: np.ndarray, counts: np.ndarray, masks: np.nd
     """Exact integer sums  S_j = sum_keys count * (-1)^{popcount(key & mask_j)}  on the device (K3)."""
     if keys.size == 0 or masks.size == 0:
         return np.zeros(masks.size, dtype=np.int64)
-    st = get_runtime().state(1)  # K3 only needs a device context
+    st = get_runtime().context_state()  # K3 only needs a device context
     return st.parity_sums(keys, masks, counts=counts)
 
 

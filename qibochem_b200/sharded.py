@@ -53,6 +53,22 @@ class ShardedState:
         self.n_swaps = 0
         self.last_passes = 0
         self.last_sweeps = 0
+        self._lambda_live = False  # adjoint gradient in progress: the scratch array (lambda) follows every re-layout
+        self.n_qubits = n_qubits  # DeviceState-compatible surface: Circuit / SymbolicHamiltonian / measurement use it
+        self.device = getattr(local, "device", 0)
+
+    @property
+    def dim(self) -> int:
+        return 1 << self.n
+
+    def synchronize(self) -> None:
+        self.local.synchronize()
+
+    def close(self) -> None:
+        if hasattr(self.ex, "close"):
+            self.ex.close()
+        if hasattr(self.local, "close"):
+            self.local.close()
 
     # ---- layout ---------------------------------------------------------------------------------------------
     def _is_global(self, logical_bit: int) -> bool:
@@ -79,7 +95,7 @@ class ShardedState:
         """Exchange a global logical bit with a local one (data movement + permutation update)."""
         pg, pl = self.pos[global_logical], self.pos[local_logical]
         assert pg >= self.nl > pl
-        self.ex.swap(pg - self.nl, pl)
+        self.ex.swap(pg - self.nl, pl, with_scratch=self._lambda_live)
         self.pos[global_logical], self.pos[local_logical] = pl, pg
         self.n_swaps += 1
 
@@ -201,6 +217,147 @@ class ShardedState:
     def norm2(self) -> float:
         return self.ex.allreduce_sum(self.local.norm2())
 
+    # ---- adjoint gradient (reference caller: qibo.derivative.parameter_shift, doc/source/tutorials/adaptive.rst:46-61)
+    def energy_gradient(self, rxmask, rzmask, angle, hxmask, hzmask, coeff, lookahead: int = 4096):
+        """``(sum_k c_k Re<psi|P_k|psi>, dE/d angle[R])`` with psi = U psi0 resident (the given rotation program was
+        applied by ``apply_pauli_rotations``); leaves psi0.  lambda = H psi is built layout by layout like
+        ``expectation``; afterwards every exchange moves psi AND lambda, and the rotations are walked backwards in
+        maximal segments whose x-masks are local."""
+        rxs = [int(v) for v in np.asarray(rxmask, dtype=np.uint64).tolist()]
+        rzs = [int(v) for v in np.asarray(rzmask, dtype=np.uint64).tolist()]
+        ang = np.asarray(angle, dtype=np.float64)
+        xs = np.asarray(hxmask, dtype=np.uint64)
+        zs = np.asarray(hzmask, dtype=np.uint64)
+        cs = np.asarray(coeff, dtype=np.float64)
+        R = len(rxs)
+        grad = np.zeros(R, dtype=np.float64)
+        if xs.size == 0:
+            return 0.0, grad
+        self.local.hpsi(np.zeros(0, np.uint64), np.zeros(0, np.uint64), np.zeros(0), accumulate=False)  # lambda = 0
+        self._lambda_live = True
+        try:
+            remaining = np.ones(xs.size, dtype=bool)
+            while remaining.any():
+                gm = np.uint64(self._global_mask())
+                ready = remaining & ((xs & gm) == 0)
+                if not ready.any():
+                    self._relayout_for_terms(xs[remaining])
+                    gm = np.uint64(self._global_mask())
+                    ready = remaining & ((xs & gm) == 0)
+                    if not ready.any():
+                        raise RuntimeError("could not find a layout that makes any remaining term local")
+                idx = np.nonzero(ready)[0]
+                px, pz, pc = self._translate_terms(xs[idx], zs[idx], cs[idx])
+                self.local.hpsi(px, pz, pc, accumulate=True)
+                remaining[idx] = False
+            energy = self.local.lambda_inner().real
+            j = R
+            while j > 0:
+                gm = self._global_mask()
+                if rxs[j - 1] & gm:
+                    self._localise(rxs[j - 1], rxs[max(0, j - 1 - lookahead) : j - 1][::-1])
+                    gm = self._global_mask()
+                i = j
+                while i > 0 and not (rxs[i - 1] & gm):
+                    i -= 1
+                px = np.empty(j - i, dtype=np.uint64)
+                pz = np.empty(j - i, dtype=np.uint64)
+                pa = np.empty(j - i, dtype=np.float64)
+                sg = np.empty(j - i, dtype=np.float64)
+                for k in range(i, j):
+                    xl, _ = self._to_physical(rxs[k])
+                    zl, zg = self._to_physical(rzs[k])
+                    px[k - i], pz[k - i] = xl, zl
+                    sg[k - i] = self._rank_sign(zg)
+                    pa[k - i] = ang[k] * sg[k - i]
+                grad[i:j] = sg * self.local.gradient_backward(px, pz, pa)  # chain rule: local angle = sign * angle
+                j = i
+        finally:
+            self._lambda_live = False
+        total = self.ex.allreduce_array(np.concatenate([[energy], grad]))
+        return float(total[0]), total[1:]
+
+    # ---- host copies (small registers / tests) -------------------------------------------------------------------
+    def from_numpy(self, state: np.ndarray) -> None:
+        """Scatter a full LOGICAL-order state: the layout is reset to the identity, rank r keeps slice r."""
+        psi = np.ascontiguousarray(np.asarray(state, dtype=np.complex128)).reshape(-1)
+        if psi.size != 1 << self.n:
+            raise ValueError("state vector has the wrong size")
+        self.pos = list(range(self.n))
+        self.local.from_numpy(psi[self.rank << self.nl : (self.rank + 1) << self.nl])
+
+    def to_numpy(self) -> np.ndarray:
+        return self.gather_logical()
+
+    # ---- K5 / K3: sampled path (SURVEY 8e: per-rank mass -> host multinomial -> per-rank shots -> integer partial
+    #      sums -> all-reduce).  Reference call site: src/qibochem/measurement/result.py:105-117 ---------------------
+    def sample(self, x_basis_mask: int, y_basis_mask: int, n_shots: int, seed: int, shot_offset: int = 0,
+               on_device: bool = True, return_total: bool = False):  # fmt: skip
+        """Draw ``n_shots`` shots of the whole register in the product basis, split over the ranks: rank r draws
+        Multinomial(n_shots, mass)[r] shots from ITS shard's conditional distribution, with Philox counters offset by
+        the shots of the lower ranks (disjoint streams).  Returns a ``ShardedSamples`` (this rank's part)."""
+        rot = int(x_basis_mask) | int(y_basis_mask)
+        if bin(rot).count("1") > self.nl:
+            raise NotImplementedError("more X/Y-measured qubits than local index bits of a shard")
+        # a basis rotation on a global bit would mix shards: make the rotated bits local first
+        self._localise(rot, [], protect_mask=0)
+        xl, xg = self._to_physical(int(x_basis_mask))
+        yl, yg = self._to_physical(int(y_basis_mask))
+        assert xg == 0 and yg == 0
+        _, mass = self.local.sample(xl, yl, 0, seed, on_device=on_device, return_total=True)
+        masses = np.array(self.ex.allgather_floats(mass), dtype=np.float64)
+        p = np.clip(masses, 0.0, None)
+        p = p / p.sum()
+        # identical on every rank: same generator, same probabilities (bit-identical after the all-gather)
+        split = np.random.default_rng([int(seed) & 0xFFFFFFFF, (int(seed) >> 32) & 0xFFFFFFFF, 0x5A17]).multinomial(int(n_shots), p)
+        mine = int(split[self.rank])
+        offset = int(shot_offset) + int(split[: self.rank].sum())
+        local = self.local.sample(xl, yl, mine, seed, shot_offset=offset, on_device=on_device) if mine else None
+        out = ShardedSamples(self, local, mine, list(self.pos), int(n_shots))
+        return (out, float(masses.sum())) if return_total else out
+
+    def _masks_to_physical(self, masks, pos):
+        """logical masks -> (local physical masks, parity of this rank's bits under the global part)."""
+        m = np.asarray(masks, dtype=np.uint64)
+        loc = np.zeros(m.size, dtype=np.uint64)
+        par = np.zeros(m.size, dtype=np.uint64)
+        one = np.uint64(1)
+        for b in range(self.n):
+            bit = (m >> np.uint64(b)) & one
+            p = pos[b]
+            if p < self.nl:
+                loc |= bit << np.uint64(p)
+            elif (self.rank >> (p - self.nl)) & 1:
+                par ^= bit
+        return loc, par
+
+    def parity_sums(self, samples: "ShardedSamples", masks, counts=None) -> np.ndarray:
+        """Exact int64 sums S_j = sum_shots (-1)^{popcount(shot & mask_j)} over ALL ranks' shots (K3 partials, the
+        global bits of a mask contribute a per-rank sign, one integer all-reduce)."""
+        if counts is not None:
+            raise NotImplementedError("weighted sums over sharded samples")
+        loc, par = self._masks_to_physical(masks, samples.pos)
+        if samples.n_local:
+            part = self.local.parity_sums(samples.local, loc)
+        else:
+            part = np.zeros(loc.size, dtype=np.int64)
+        part = np.where(par == 1, -part, part).astype(np.int64)
+        return self.ex.allreduce_int64(part)
+
+    def frequencies(self, samples: "ShardedSamples", keep_mask: int):
+        """Histogram over the ``keep_mask`` bits (logical index-bit positions) of all ranks' shots -> (keys compacted
+        like DeviceState.frequencies, ascending; counts)."""
+        idx = samples.logical_indices_all_ranks()
+        kept = [b for b in range(self.n) if (int(keep_mask) >> b) & 1]
+        comp = np.zeros(idx.size, dtype=np.uint64)
+        for j, b in enumerate(kept):
+            comp |= ((idx >> np.uint64(b)) & np.uint64(1)) << np.uint64(j)
+        keys, counts = np.unique(comp, return_counts=True)
+        return keys.astype(np.uint64), counts.astype(np.int64)
+
+    def outcome_variance(self, keys, counts, masks, coeffs, mean: float):
+        return self.local.outcome_variance(keys, counts, masks, coeffs, mean)  # host arrays in, rank-independent
+
     # ---- tests / small registers ------------------------------------------------------------------------------
     def gather_logical(self) -> np.ndarray:
         """Full state in LOGICAL index order on every rank (small n only; used by tests)."""
@@ -211,6 +368,37 @@ class ShardedState:
         for b in range(self.n):
             phys |= ((idx >> np.uint64(b)) & np.uint64(1)) << np.uint64(self.pos[b])
         return full_phys[phys]
+
+
+class ShardedSamples:
+    """This rank's part of a sharded measurement: local physical outcome indices + the layout they were drawn in."""
+
+    def __init__(self, state: ShardedState, local, n_local: int, pos: list[int], n_total: int):
+        self.state, self.local, self.n_local, self.pos, self.n_total = state, local, n_local, pos, n_total
+
+    def _local_numpy(self) -> np.ndarray:
+        if not self.n_local:
+            return np.zeros(0, dtype=np.uint64)
+        loc = self.local
+        if hasattr(loc, "cpu"):
+            loc = loc.cpu().numpy()
+        return np.asarray(loc).astype(np.uint64)
+
+    def logical_indices_all_ranks(self) -> np.ndarray:
+        """All shots of the measurement as LOGICAL full-register indices, rank-major (identical on every rank)."""
+        st = self.state
+        phys = self._local_numpy() | (np.uint64(st.rank) << np.uint64(st.nl))
+        logical = np.zeros(phys.size, dtype=np.uint64)
+        for b in range(st.n):
+            logical |= ((phys >> np.uint64(self.pos[b])) & np.uint64(1)) << np.uint64(b)
+        parts = st.ex.allgather_object(logical)
+        return np.concatenate(parts) if parts else logical
+
+    def cpu(self):
+        return self
+
+    def numpy(self) -> np.ndarray:
+        return self.logical_indices_all_ranks()
 
 
 class IpcExchanger:
@@ -226,6 +414,7 @@ class IpcExchanger:
         handles = [None] * world
         dist.all_gather_object(handles, state.ipc_export())
         self.peer = {r: state.ipc_open(handles[r]) for r in range(world) if r != rank}
+        self.peer_scratch: dict[int, int] = {}  # opened lazily: only the adjoint gradient moves the scratch arrays
         self._buf = torch.zeros(1, dtype=torch.float64, device=f"cuda:{device}")
         self.swap_seconds = 0.0
         self.swap_bytes = 0
@@ -235,22 +424,52 @@ class IpcExchanger:
         self.dist.all_reduce(self._buf)  # NCCL barrier on torch's stream
         self.torch.cuda.current_stream().synchronize()
 
-    def swap(self, global_k: int, local_pos: int) -> None:
+    def _open_scratch_peers(self) -> None:
+        handles = [None] * self.world
+        self.dist.all_gather_object(handles, self.state.ipc_export_scratch())
+        self.peer_scratch = {r: self.state.ipc_open(handles[r]) for r in range(self.world) if r != self.rank}
+
+    def swap(self, global_k: int, local_pos: int, with_scratch: bool = False) -> None:
         import time
 
+        if with_scratch and not self.peer_scratch:
+            self._open_scratch_peers()
         partner = self.rank ^ (1 << global_k)
         side = (self.rank >> global_k) & 1
         self.barrier()  # both shards idle and consistent
         t0 = time.perf_counter()
         self.state.swap_with_peer(self.peer[partner], local_pos, side, side)
+        if with_scratch:
+            self.state.swap_scratch_with_peer(self.peer_scratch[partner], local_pos, side, side)
         self.barrier()  # both halves of the exchange have landed
         self.swap_seconds += time.perf_counter() - t0
-        self.swap_bytes += self.state.dim * 16 // 2  # bytes leaving (= entering) this GPU
+        self.swap_bytes += self.state.dim * 16 // 2 * (2 if with_scratch else 1)  # bytes leaving (= entering) this GPU
 
     def allreduce_sum(self, value: float) -> float:
         t = self.torch.tensor([value], dtype=self.torch.float64, device=f"cuda:{self.device}")
         self.dist.all_reduce(t)
         return float(t.item())
+
+    def allreduce_array(self, values: np.ndarray) -> np.ndarray:
+        t = self.torch.from_numpy(np.ascontiguousarray(values, dtype=np.float64)).to(f"cuda:{self.device}")
+        self.dist.all_reduce(t)
+        return t.cpu().numpy()
+
+    def allreduce_int64(self, values: np.ndarray) -> np.ndarray:
+        t = self.torch.from_numpy(np.ascontiguousarray(values, dtype=np.int64)).to(f"cuda:{self.device}")
+        self.dist.all_reduce(t)
+        return t.cpu().numpy()
+
+    def allgather_floats(self, value: float) -> list[float]:
+        t = self.torch.tensor([value], dtype=self.torch.float64, device=f"cuda:{self.device}")
+        out = [self.torch.empty_like(t) for _ in range(self.world)]
+        self.dist.all_gather(out, t)
+        return [float(o.item()) for o in out]
+
+    def allgather_object(self, obj) -> list:
+        out = [None] * self.world
+        self.dist.all_gather_object(out, obj)
+        return out
 
     def allgather_array(self, arr: np.ndarray) -> np.ndarray:
         t = self.torch.from_numpy(np.ascontiguousarray(arr).view(np.float64)).to(f"cuda:{self.device}")
@@ -260,6 +479,6 @@ class IpcExchanger:
 
     def close(self) -> None:
         self.barrier()
-        for p in self.peer.values():
+        for p in list(self.peer.values()) + list(self.peer_scratch.values()):
             self.state.ipc_close(p)
-        self.peer = {}
+        self.peer, self.peer_scratch = {}, {}

@@ -107,6 +107,26 @@ def test_set_parameters_updates_compiled_program():
     assert len(d.get_parameters()) == 10 and len(c.get_parameters()) == 9
 
 
+def test_set_parameters_with_gates_that_lower_to_several_rotations():
+    """A controlled RY / GIVENS / GeneralizedRBS lowers to several rotations sharing ONE parameter: the compiled
+    program's fast path must index the parameter vector by the owning gate (it used to broadcast by rotation)."""
+    from qibochem_b200.ansatz import givens_circuit, qeb_circuit
+
+    for build in (qeb_circuit, givens_circuit):
+        c = build(6, [0, 1, 2, 3], 0.1) + build(6, [0, 4], 0.2) + build(6, [1, 2, 4, 5], 0.3)
+        c.add(gates.RZ(0, 0.4))
+        assert len(c.get_parameters()) == 4
+        prog = c.program()
+        assert prog.param_rot.size > 4 and prog.param_owner.max() == 3
+        new = np.array([0.7, -0.3, 0.25, 1.1])
+        c.set_parameters(new)  # second call: the cached program is patched in place
+        assert c.program() is prog
+        fresh = c.copy().program()  # compiled from the gates' (already updated) parameters
+        assert np.allclose(prog.angle, fresh.angle, atol=0, rtol=0)
+        assert np.array_equal(prog.xmask, fresh.xmask) and np.array_equal(prog.zmask, fresh.zmask)
+        assert [p for (p,) in c.get_parameters()] == pytest.approx(list(new))
+
+
 def test_ansatz_argument_checks():
     """tests/test_ansatz.py:612-638 of the reference (the parts on the hot path)."""
     for fn in (hf_circuit, ucc_circuit):

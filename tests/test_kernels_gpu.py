@@ -613,3 +613,95 @@ def test_register_phase_rotations_edge_cases(DeviceState, n):
             st.from_numpy(psi)
             st.apply_pauli_rotations(xs, zs, phis)
             assert np.abs(st.to_numpy() - ref).max() < AMP_TOL, f"k1_mode={mode}"
+
+
+def test_tiled_plan_cache_compares_term_lists(DeviceState):
+    """The tiled plan bakes the coefficients in and is cached per handle: H, -H and H with two signs flipped used to
+    hash alike (word-wise xor-multiply keeps bit 63 in bit 63) and silently reuse H's plan."""
+    from qibochem_b200 import synthetic
+
+    n = 16
+    psi = random_state(n, 77)
+    hx, hz, hc, _ = synthetic.molecular_like_hamiltonian(n, 2000)
+    if hc.size % 2:
+        hx, hz, hc = hx[:-1], hz[:-1], hc[:-1]
+    flipped = hc.copy()
+    flipped[[3, 700]] *= -1.0
+    scaled = hc * 4.0  # exponent-only change
+    with DeviceState(n) as st:
+        st.from_numpy(psi)
+        st.set_option("k2_mode", 1)
+        ref = {name: st.expectation(hx, hz, c) for name, c in (("h", hc), ("neg", -hc), ("flip", flipped), ("x4", scaled))}
+        st.set_option("k2_mode", 0)  # n >= 16, T >= 512: tiles
+        got = {name: st.expectation(hx, hz, c) for name, c in (("h", hc), ("neg", -hc), ("flip", flipped), ("x4", scaled), ("h2", hc))}
+    assert abs(ref["neg"] + ref["h"]) < E_TOL and abs(ref["flip"] - ref["h"]) > 1e-6
+    for name in ("h", "neg", "flip", "x4"):
+        assert abs(got[name] - ref[name]) < E_TOL, name
+    assert got["h2"] == got["h"]
+
+
+def test_tiled_expectation_with_many_leftover_groups(DeviceState):
+    """More leftover x-groups (too wide for a tile) than the result buffer's initial capacity: growing it while the
+    tiled sum already sits in slot 0 must keep that sum."""
+    from qibochem_b200 import synthetic
+
+    n = 16
+    rng = np.random.default_rng(5)
+    psi = random_state(n, 78)
+    hx, hz, hc, _ = synthetic.molecular_like_hamiltonian(n, 1500)
+    wide = set()
+    while len(wide) < 1200:
+        bits = rng.choice(n, size=14, replace=False)
+        wide.add(int(sum(1 << int(b) for b in bits)) | 1 << 15)
+    wx = np.array(sorted(wide), dtype=np.uint64)
+    wz = rng.integers(0, 2**n, size=wx.size, dtype=np.uint64)
+    wc = rng.normal(scale=0.05, size=wx.size)
+    ax, az, ac = np.concatenate([hx, wx]), np.concatenate([hz, wz]), np.concatenate([hc, wc])
+    with DeviceState(n) as st:  # fresh handle: result buffer at its initial capacity
+        st.from_numpy(psi)
+        st.set_option("k2_mode", 2)
+        e_tiled = st.expectation(ax, az, ac)
+        st.set_option("k2_mode", 1)
+        e_sweeps = st.expectation(ax, az, ac)
+    from oracle import oracle_c as OC
+
+    ref = OC.expectation_masks(psi, n, ax, az, ac)
+    assert abs(e_sweeps - ref) < E_TOL and abs(e_tiled - ref) < E_TOL
+
+
+def test_bench_generators_26q_against_oracle(DeviceState):
+    """The benchmark's own generators (UCCSD prefix + 100 000-term molecular-structured Hamiltonian) at 26 qubits:
+    per-term values of a random 1000-term subset against the C oracle on the SAME state (copied back), the tiled
+    energy of that subset against the oracle sum, and the full 10^5-term tiled energy against the per-x-mask sweeps."""
+    import torch
+
+    if torch.cuda.get_device_properties(0).total_memory < 8e9:
+        pytest.skip("needs > 8 GB of HBM")
+    from oracle import oracle_c as OC
+    from qibochem_b200 import synthetic
+
+    n, ne = 26, 12
+    OC.set_num_threads(0)
+    rx, rz, ra, _ = synthetic.uccsd_rotation_stream(n, ne, max_excitations=64)
+    hx, hz, hc, const = synthetic.molecular_like_hamiltonian(n, 100_000)
+    n_sub = 1000 if OC.num_threads() >= 12 else 300
+    sub = np.sort(np.random.default_rng(26).choice(hx.size, size=n_sub, replace=False))
+    with DeviceState(n) as st:
+        st.set_basis_state(synthetic.hf_index(n, ne))
+        st.apply_pauli_rotations(rx, rz, ra)
+        e_sub_pt, per_term = st.expectation(hx[sub], hz[sub], hc[sub], per_term=True)
+        st.set_option("k2_mode", 2)
+        e_sub_tiled = st.expectation(hx[sub], hz[sub], hc[sub])
+        e_full_tiled = st.expectation(hx, hz, hc)
+        passes = st.last_sweeps
+        st.set_option("k2_mode", 1)
+        e_full_sweeps = st.expectation(hx, hz, hc)
+        sweeps = st.last_sweeps
+        psi = st.to_numpy()
+    assert abs(np.vdot(psi, psi).real - 1.0) < 1e-12
+    ref_terms = OC.expectation_masks_per_term(psi, n, hx[sub], hz[sub])
+    assert np.abs(per_term - ref_terms).max() < 1e-12
+    ref_sub = float(np.dot(hc[sub], ref_terms))
+    assert abs(e_sub_pt - ref_sub) < E_TOL and abs(e_sub_tiled - ref_sub) < E_TOL
+    assert passes < sweeps / 20
+    assert abs(e_full_tiled - e_full_sweeps) < E_TOL

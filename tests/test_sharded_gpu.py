@@ -27,12 +27,21 @@ class ThreadExchanger:
         self.states[self.rank].synchronize()
         self.bar.wait()
 
-    def swap(self, global_k, local_pos):
+    def swap(self, global_k, local_pos, with_scratch=False):
         partner = self.rank ^ (1 << global_k)
         side = (self.rank >> global_k) & 1
         self.barrier()
         self.states[self.rank].swap_with_peer(self.states[partner].device_ptr, local_pos, side, side)
+        if with_scratch:
+            self.states[self.rank].swap_scratch_with_peer(self.states[partner].scratch_device_ptr, local_pos, side, side)
         self.barrier()
+
+    def allreduce_array(self, values):
+        self.slots[self.rank] = np.array(values, dtype=np.float64)
+        self.bar.wait()
+        total = sum(self.slots[r] for r in range(self.world))
+        self.bar.wait()
+        return total
 
     def allreduce_sum(self, value):
         self.slots[self.rank] = value
