@@ -19,6 +19,11 @@ NVCC_FLAGS = [
 ]  # fmt: skip
 
 
+def extra_flags() -> list[str]:
+    """Extra -D flags for kernel A/B experiments (tools/): QC_NVCC_DEFINES="QC_K2T_PACE=8 FOO=1"."""
+    return [f"-D{d}" for d in os.environ.get("QC_NVCC_DEFINES", "").split()]
+
+
 def find_nvcc() -> str:
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
@@ -37,12 +42,16 @@ def needs_build() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
-    cmd = [find_nvcc(), *NVCC_FLAGS, "-shared", "-o", LIB, *[os.path.join(CSRC, s) for s in SOURCES]]
+    tmp = LIB + f".tmp{os.getpid()}"  # built aside and renamed: a reader never sees a half-written library
+    cmd = [find_nvcc(), *NVCC_FLAGS, *extra_flags(), "-shared", "-o", tmp, *[os.path.join(CSRC, s) for s in SOURCES]]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or proc.returncode:
         sys.stderr.write(proc.stdout + proc.stderr)
     if proc.returncode:
+        if os.path.exists(tmp):
+            os.unlink(tmp)
         raise RuntimeError("nvcc failed building libqibochem_b200.so")
+    os.replace(tmp, LIB)
     with open(os.path.join(HERE, "csrc", "ptxas_info.txt"), "w") as f:  # registers / spills / shared memory per kernel
         f.write("".join(line for line in proc.stderr.splitlines(keepends=True) if "Compile time" not in line))
     return LIB

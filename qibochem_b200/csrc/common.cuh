@@ -45,6 +45,8 @@ enum KernelClass { kK0Init = 0, kK1Rotation = 1, kK2Expectation = 2, kReduce = 3
 
 struct TiledPlan;  // expectation_tiled.cu
 void free_tiled_plan(TiledPlan* p);
+struct HpPlan;     // gradient_tiled.cu
+void free_hp_plan(HpPlan* p);
 
 struct Profiler {
     bool enabled = false;
@@ -85,6 +87,7 @@ struct qc_state {
     qc::Profiler prof;
     uint64_t h2d_bytes = 0, d2h_bytes = 0;  // host<->device bytes moved by the product path since the last reset
     std::vector<qc::TiledPlan*> k2plans;  // cached plans of the tiled expectation (keyed by a hash of the term list; LRU)
+    qc::HpPlan* hp_plan = nullptr;        // cached plan of the tiled H|psi> (adjoint gradient), last term list only
     int k1_mode = 0;                  // 0 auto, 1 one HBM pass per fused run, 2 shared-memory tiles whenever a run fits
     int k2_mode = 0;                  // 0 auto, 1 force sweeps (one HBM pass per x-mask), 2 force tiles
     int ensure_partials(size_t doubles);

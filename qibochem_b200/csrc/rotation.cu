@@ -121,6 +121,49 @@ __global__ void __launch_bounds__(kThreads) rot_diag_kernel(double2* __restrict_
     }
 }
 
+// ---- small registers (n <= kSmallMaxQubits): the WHOLE program in one launch, state in shared memory ---------------
+// A 12-qubit LiH-sized UCCSD program is ~90 fused runs over a 64 KB state: one launch per run makes it launch-bound
+// (~6 us per run).  Here ONE CTA of 1024 threads keeps the state in shared memory and applies every run of the call in
+// order (one __syncthreads per run); reference behaviour replaced: the 15 108 gate passes of qibo's gate loop for the
+// 12-qubit circuit_ansatz.
+constexpr int kSmallMaxQubits = 13;   // 2^13 x 16 B = 128 KB of shared memory
+constexpr int kSmallThreads = 1024;
+
+__global__ void __launch_bounds__(kSmallThreads, 1)
+    rot_small_kernel(double2* __restrict__ psi, int n, int n_runs, const RotDesc* __restrict__ descs,
+                     const double2* __restrict__ table) {
+    extern __shared__ __align__(16) unsigned char small_raw[];
+    double2* s = reinterpret_cast<double2*>(small_raw);
+    const uint32_t dim = 1u << n, npairs = dim >> 1;
+    for (uint32_t i = threadIdx.x; i < dim; i += kSmallThreads) s[i] = psi[i];
+    __syncthreads();
+    for (int r = 0; r < n_runs; ++r) {
+        const RotDesc d = descs[r];  // warp-uniform loads
+        const double2* tab = table + d.table_off;
+        if (d.x == 0) {
+            for (uint32_t i = threadIdx.x; i < dim; i += kSmallThreads) {
+                const double2 cs = __ldg(&tab[d.sup_mask ? gather_bits(i, d.sup_mask) : 0u]);
+                const double ms = -flip_sign(cs.y, i, d.z0);
+                const double2 a = s[i];
+                s[i] = make_double2(cs.x * a.x - ms * a.y, cs.x * a.y + ms * a.x);
+            }
+        } else {
+            for (uint32_t p = threadIdx.x; p < npairs; p += kSmallThreads) {
+                const uint32_t i = (uint32_t)insert_zero_bit(p, d.hb), j = i ^ (uint32_t)d.x;
+                const double2 a = s[i], b = s[j];
+                const double2 cs = __ldg(&tab[d.sup_mask ? gather_bits(i, d.sup_mask) : 0u]);
+                const double f = flip_sign(cs.y, i, d.z0);
+                const double2 wb = cmul(d.war, d.wai, b);
+                const double2 wa = cmul(d.wbr, d.wbi, a);
+                s[i] = make_double2(cs.x * a.x + f * wb.x, cs.x * a.y + f * wb.y);
+                s[j] = make_double2(cs.x * b.x + f * wa.x, cs.x * b.y + f * wa.y);
+            }
+        }
+        __syncthreads();
+    }
+    for (uint32_t i = threadIdx.x; i < dim; i += kSmallThreads) psi[i] = s[i];
+}
+
 // ---- K1T: a BATCH of consecutive fused runs applied in one in-place HBM pass --------------------------------------
 // When the x-masks of consecutive runs fit, together with index bits 0..2 (128-byte runs in HBM), into a set S of 12
 // index bits, a CTA stages the 4096 amplitudes that differ only in the S bits (64 KB) in shared memory, applies every
@@ -476,6 +519,61 @@ int apply_rotations_to(qc_state* h, double2* target, size_t R, const uint64_t* x
                        const double* angle, int k1_mode, int* n_passes_out) {
     std::vector<Run> runs;
     plan_runs(R, xmask, zmask, runs);
+
+    if (h->n <= kSmallMaxQubits && k1_mode == 0 && runs.size() >= 2) {
+        // ---- small register: every run of the call in ONE launch, state in shared memory
+        size_t total_entries = 0;
+        for (const Run& g : runs) total_entries += (size_t)1 << __builtin_popcountll(g.sup);
+        const size_t bytes_desc = (runs.size() * sizeof(RotDesc) + 255) & ~(size_t)255;
+        QC_CHECK(cudaStreamSynchronize(h->stream));
+        if (h->arena.ensure(bytes_desc + total_entries * sizeof(double2))) return 1;
+        RotDesc* hdesc = (RotDesc*)h->arena.host;
+        double2* htab = (double2*)((char*)h->arena.host + bytes_desc);
+        size_t off = 0;
+        for (size_t gi = 0; gi < runs.size(); ++gi) {
+            const Run& g = runs[gi];
+            int sup_bits[kMaxSupport], nsup = 0;
+            for (uint64_t m = g.sup; m; m &= m - 1) sup_bits[nsup++] = __builtin_ctzll(m);
+            const int ny0 = __builtin_popcountll(g.x & g.z0);
+            for (uint32_t pat = 0; pat < (1u << nsup); ++pat) {
+                uint64_t bits = 0;
+                for (int k = 0; k < nsup; ++k)
+                    if ((pat >> k) & 1u) bits |= 1ull << sup_bits[k];
+                double phi = 0.0;
+                for (size_t k = 0; k < g.count; ++k) {
+                    const size_t r = g.first + k;
+                    const uint64_t dz = zmask[r] ^ g.z0;
+                    const int nyk = __builtin_popcountll(g.x & zmask[r]);
+                    double sg = ((((nyk - ny0) % 4) + 4) % 4 == 0) ? 1.0 : -1.0;
+                    if (__builtin_popcountll(bits & dz) & 1) sg = -sg;
+                    phi += sg * angle[r];
+                }
+                htab[off + pat] = make_double2(cos(0.5 * phi), sin(0.5 * phi));
+            }
+            RotDesc& d = hdesc[gi];
+            memset(&d, 0, sizeof(d));
+            d.x = g.x;
+            d.z0 = g.z0;
+            d.sup_mask = g.sup;
+            d.hb = g.hb;
+            pow_minus_i(ny0 + 1, d.war, d.wai);
+            pow_minus_i(1 - ny0, d.wbr, d.wbi);
+            d.table_off = (uint32_t)off;
+            off += (size_t)1 << nsup;
+        }
+        QC_CHECK(cudaMemcpyAsync(h->arena.dev, h->arena.host, bytes_desc + total_entries * sizeof(double2), cudaMemcpyHostToDevice, h->stream));
+        h->h2d_bytes += bytes_desc + total_entries * sizeof(double2);
+        const size_t smem = (size_t)h->dim * sizeof(double2);
+        QC_CHECK(cudaFuncSetAttribute(rot_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
+        {
+            LaunchScope ls(h, kK1Rotation, 32.0 * (double)h->dim * (double)runs.size());
+            rot_small_kernel<<<1, kSmallThreads, smem, h->stream>>>(target, h->n, (int)runs.size(), (const RotDesc*)h->arena.dev,
+                                                                  (const double2*)((const char*)h->arena.dev + bytes_desc));
+        }
+        QC_CHECK(cudaGetLastError());
+        if (n_passes_out) *n_passes_out = 1;
+        return 0;
+    }
 
     // ---- batches.  k1_mode 0 (auto) / 3: register-blocked PHASES (K1O): consecutive runs whose distinct x-masks are
     // linearly independent (<= 5 of them); 2: shared-memory TILES (K1T): consecutive runs whose x-masks fit, with index

@@ -20,6 +20,30 @@ from __future__ import annotations
 import numpy as np
 
 
+def _planner_stats_fn():
+    """``f(n_local, x, z, c) -> uint64[16]`` over the native planner (host-only), or None when the library is absent
+    (CPU tests of the host logic with stand-in shards)."""
+    try:
+        import ctypes as C
+
+        from qibochem_b200 import _native
+
+        lib = _native.load()
+    except Exception:
+        return None
+    u64p, f64p = C.POINTER(C.c_uint64), C.POINTER(C.c_double)
+
+    def stats(n_local, x, z, c):
+        x, z = np.ascontiguousarray(x, dtype=np.uint64), np.ascontiguousarray(z, dtype=np.uint64)
+        c = np.ascontiguousarray(c, dtype=np.float64)
+        out = np.zeros(16, dtype=np.uint64)
+        _native.check(lib.qc_k2_plan_stats(int(n_local), x.size, x.ctypes.data_as(u64p), z.ctypes.data_as(u64p), c.ctypes.data_as(f64p),
+                                           out.ctypes.data_as(u64p), None), "qc_k2_plan_stats")  # fmt: skip
+        return out
+
+    return stats
+
+
 def _bits(mask: int):
     b = 0
     while mask >> b:
@@ -53,6 +77,8 @@ class ShardedState:
         self.n_swaps = 0
         self.last_passes = 0
         self.last_sweeps = 0
+        self._layout_cache: dict = {}
+        self._plan_stats = _planner_stats_fn()
         self._lambda_live = False  # adjoint gradient in progress: the scratch array (lambda) follows every re-layout
         self.n_qubits = n_qubits  # DeviceState-compatible surface: Circuit / SymbolicHamiltonian / measurement use it
         self.device = getattr(local, "device", 0)
@@ -169,15 +195,18 @@ class ShardedState:
         remaining = np.ones(xs.size, dtype=bool)
         partial = 0.0
         sweeps = 0
+        first = True
         while remaining.any():
             gm = np.uint64(self._global_mask())
             ready = remaining & ((xs & gm) == 0)
-            if not ready.any():
-                self._relayout_for_terms(xs[remaining])
+            if not ready.any() or (first and self._plan_stats is not None):
+                # the rotations leave an arbitrary layout: the first one is chosen like every later one
+                self._relayout_for_terms(xs[remaining], zs[remaining], cs[remaining])
                 gm = np.uint64(self._global_mask())
                 ready = remaining & ((xs & gm) == 0)
                 if not ready.any():
                     raise RuntimeError("could not find a layout that makes any remaining term local")
+            first = False
             idx = np.nonzero(ready)[0]
             px, pz, pc = self._translate_terms(xs[idx], zs[idx], cs[idx])
             partial += self.local.expectation(px, pz, pc)
@@ -203,16 +232,57 @@ class ShardedState:
                 par ^= zb
         return px, pz, np.where(par == 1, -cs, cs)
 
-    def _relayout_for_terms(self, xs_remaining: np.ndarray) -> None:
-        """Choose as global the g logical bits on which the fewest remaining terms pair, then swap them out."""
+    def _relayout_for_terms(self, xs_remaining: np.ndarray, zs_remaining=None, cs_remaining=None) -> None:
+        """Choose the next set of g global logical bits for the remaining terms and swap it in.
+
+        Baseline rule: the g bits on which the fewest remaining terms pair (most terms become local).  When the shard is
+        large enough for the tiled expectation, the candidates -- every g-subset of the 2g least-used bits, plus the
+        current layout -- are priced with the tile planner itself (``qc_k2_plan_stats`` is host-only): passes, sub-cube
+        visits and records of the terms that the candidate makes local, through the per-pass cost model fitted to the
+        kernel, plus the exchanges it needs; the cheapest per served x-mask wins.  The choice is cached
+        (every energy evaluation walks through the same sequence of layouts)."""
         usage = [(int(((xs_remaining >> np.uint64(b)) & np.uint64(1)).sum()), b) for b in range(self.n)]
         usage.sort()
-        want_global = [b for _, b in usage[: self.g]]
         cur_global = [b for b in range(self.n) if self._is_global(b)]
+        want_global = [b for _, b in usage[: self.g]]
+        if zs_remaining is not None and self.nl >= 16 and xs_remaining.size >= 512 and self.g <= 3 and self._plan_stats is not None:
+            key = (hash(xs_remaining.tobytes()), hash(zs_remaining.tobytes()), tuple(cur_global))
+            cached = self._layout_cache.get(key)
+            if cached is None:
+                cached = self._price_layouts(xs_remaining, zs_remaining, cs_remaining, [b for _, b in usage[: 2 * self.g]], cur_global)
+                self._layout_cache[key] = cached
+            want_global = list(cached)
         incoming = [b for b in cur_global if b not in want_global]  # become local
         outgoing = [b for b in want_global if b not in cur_global]  # become global
         for gb, lb in zip(incoming, outgoing):
             self._swap(gb, lb)
+
+    def _price_layouts(self, xs, zs, cs, candidates, cur_global):
+        from itertools import combinations
+
+        best = None
+        sets = [tuple(sorted(c)) for c in combinations(candidates, self.g)]
+        if tuple(sorted(cur_global)) not in sets:
+            sets.append(tuple(sorted(cur_global)))
+        for G in sets:
+            gm = np.uint64(sum(1 << b for b in G))
+            sel = (xs & gm) == 0
+            if not sel.any():
+                continue
+            # masks with the global bits squeezed out (any bijection onto the local positions prices the same plan shape)
+            local_bits = [b for b in range(self.n) if b not in G]
+            px = np.zeros(int(sel.sum()), dtype=np.uint64)
+            pz = np.zeros_like(px)
+            for p, b in enumerate(local_bits):
+                px |= ((xs[sel] >> np.uint64(b)) & np.uint64(1)) << np.uint64(p)
+                pz |= ((zs[sel] >> np.uint64(b)) & np.uint64(1)) << np.uint64(p)
+            st = self._plan_stats(self.nl, px, pz, cs[sel])
+            n_x, passes, visits, dots = int(st[0]), int(st[2]), int(st[3]), int(st[4])
+            swaps = len(set(G) - set(cur_global))
+            cost = (2.69 * passes + 0.446 * visits + 0.139 * dots + 14.0 * swaps) / max(1, n_x)  # ms at 30 local qubits
+            if best is None or cost < best[0]:
+                best = (cost, G)
+        return best[1] if best else tuple(cur_global)
 
     def norm2(self) -> float:
         return self.ex.allreduce_sum(self.local.norm2())

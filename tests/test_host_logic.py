@@ -388,3 +388,47 @@ def test_native_grouping_equals_numpy_restatement(native_lib, qubitwise):
                     else:
                         assert bin((xa & zb) ^ (za & xb)).count("1") % 2 == 0
     assert group_commuting_masks([], [], qubitwise) == []
+
+
+def _paper_givens_single(q, theta):
+    """Gate list of the reference's own control circuit for a Givens single excitation (Arrazola et al. 2022; the
+    reference restates it at tests/test_ansatz.py:221-238 and asserts it equal to qibo's ``gates.GIVENS``)."""
+    return [("CNOT", (q[0], q[1]), None), ("RY", (q[0],), 0.5 * theta), ("CNOT", (q[1], q[0]), None),
+            ("RY", (q[0],), -0.5 * theta), ("CNOT", (q[1], q[0]), None), ("CNOT", (q[0], q[1]), None)]  # fmt: skip
+
+
+def _paper_givens_double(q, theta):
+    """The same for the double excitation (reference tests/test_ansatz.py:241-281 -> ``GeneralizedRBS(in, out, -theta)``)."""
+    cx, h, ry = (lambda a, b: ("CNOT", (q[a], q[b]), None)), (lambda a: ("H", (q[a],), None)), (lambda a, f: ("RY", (q[a],), f * theta))
+    return [cx(2, 3), cx(0, 2), h(0), h(3), cx(0, 1), cx(2, 3), ry(0, -0.125), ry(1, 0.125), cx(0, 3), h(3), cx(3, 1),
+            ry(0, -0.125), ry(1, 0.125), cx(2, 1), cx(2, 0), ry(0, 0.125), ry(1, -0.125), cx(3, 1), h(3), cx(0, 3),
+            ry(0, 0.125), ry(1, -0.125), cx(0, 1), cx(2, 0), h(0), h(3), cx(0, 2), cx(2, 3)]  # fmt: skip
+
+
+@pytest.mark.parametrize("excitation", [[0, 2], [0, 1, 2, 3], [1, 3], [0, 2, 1, 3]])
+def test_givens_sign_pinned_by_reference_decomposition_on_every_basis_state(excitation):
+    """The reference's test (tests/test_ansatz.py:284-300) compares ``givens_circuit`` with the paper's CNOT/RY/H
+    decomposition but only from the vacuum, which both leave alone.  Here the SAME decomposition is executed by the
+    oracle's gate path on EVERY basis state and a random state, which pins the DIRECTION of the rotation of ``GIVENS``
+    and ``GeneralizedRBS`` (including the ``-theta`` the reference passes for doubles, ansatz.py:432).  The paper's gates
+    rotate by theta / 2 (PennyLane's convention) while qibo's matrices rotate by theta [recalled], a difference the
+    reference's vacuum-only test cannot see: the control circuit is therefore built with 2 theta, and the angle SCALE
+    stays "parity unpinned"."""
+    from qibochem_b200.ansatz import givens_circuit
+
+    n, theta = 4, 0.27183
+    q = sorted(excitation)
+    control = _paper_givens_single(q, 2.0 * theta) if len(q) == 2 else _paper_givens_double(q, 2.0 * theta)
+    circuit = givens_circuit(n, excitation, theta)
+    rng = np.random.default_rng(4)
+    rand = rng.normal(size=2**n) + 1j * rng.normal(size=2**n)
+    states = [np.eye(2**n, dtype=complex)[k] for k in range(2**n)] + [rand / np.linalg.norm(rand)]
+    moved = 0
+    for psi0 in states:
+        ref = psi0.copy()
+        for name, qubits, param in control:
+            ref = O.apply_gate(ref, n, O.gate_matrix(name, param), qubits)
+        got = run_program_with_oracle(circuit, psi0)
+        assert np.abs(got - ref).max() < 1e-13
+        moved += int(np.abs(ref - psi0).max() > 1e-3)
+    assert moved >= 3  # the rotated pair of determinants and the random state really move

@@ -645,15 +645,14 @@ def test_tiled_expectation_with_many_leftover_groups(DeviceState):
     tiled sum already sits in slot 0 must keep that sum."""
     from qibochem_b200 import synthetic
 
-    n = 16
+    n = 17
     rng = np.random.default_rng(5)
     psi = random_state(n, 78)
     hx, hz, hc, _ = synthetic.molecular_like_hamiltonian(n, 1500)
-    wide = set()
-    while len(wide) < 1200:
-        bits = rng.choice(n, size=14, replace=False)
-        wide.add(int(sum(1 << int(b) for b in bits)) | 1 << 15)
-    wx = np.array(sorted(wide), dtype=np.uint64)
+    from itertools import combinations
+
+    all_wide = [sum(1 << b for b in c) for c in combinations(range(n), 13)]  # C(17, 13) = 2380 masks wider than a tile
+    wx = np.array(sorted(rng.choice(all_wide, size=1200, replace=False).tolist()), dtype=np.uint64)
     wz = rng.integers(0, 2**n, size=wx.size, dtype=np.uint64)
     wc = rng.normal(scale=0.05, size=wx.size)
     ax, az, ac = np.concatenate([hx, wx]), np.concatenate([hz, wz]), np.concatenate([hc, wc])
@@ -670,9 +669,10 @@ def test_tiled_expectation_with_many_leftover_groups(DeviceState):
 
 
 def test_bench_generators_26q_against_oracle(DeviceState):
-    """The benchmark's own generators (UCCSD prefix + 100 000-term molecular-structured Hamiltonian) at 26 qubits:
-    per-term values of a random 1000-term subset against the C oracle on the SAME state (copied back), the tiled
-    energy of that subset against the oracle sum, and the full 10^5-term tiled energy against the per-x-mask sweeps."""
+    """The benchmark's own generators (UCCSD prefix + molecular-structured Hamiltonian; 76 000 terms is all a 26-qubit
+    register offers: every 4-set is used) at 26 qubits: per-term values of a random 1000-term subset against the C
+    oracle on the SAME state (copied back), the tiled energy of that subset against the oracle sum, and the full
+    tiled energy against the per-x-mask sweeps."""
     import torch
 
     if torch.cuda.get_device_properties(0).total_memory < 8e9:
@@ -683,7 +683,7 @@ def test_bench_generators_26q_against_oracle(DeviceState):
     n, ne = 26, 12
     OC.set_num_threads(0)
     rx, rz, ra, _ = synthetic.uccsd_rotation_stream(n, ne, max_excitations=64)
-    hx, hz, hc, const = synthetic.molecular_like_hamiltonian(n, 100_000)
+    hx, hz, hc, const = synthetic.molecular_like_hamiltonian(n, 76_000)
     n_sub = 1000 if OC.num_threads() >= 12 else 300
     sub = np.sort(np.random.default_rng(26).choice(hx.size, size=n_sub, replace=False))
     with DeviceState(n) as st:
@@ -705,3 +705,84 @@ def test_bench_generators_26q_against_oracle(DeviceState):
     assert abs(e_sub_pt - ref_sub) < E_TOL and abs(e_sub_tiled - ref_sub) < E_TOL
     assert passes < sweeps / 20
     assert abs(e_full_tiled - e_full_sweeps) < E_TOL
+
+
+def _hpsi_inputs(n, seed):
+    """Hamiltonian for the tiled H|psi>: molecular-structured terms (quads, hopping groups with ~2n z-masks each, the
+    diagonal group) + random strings with odd nY (Im-type weights), several z-masks per x-mask, and x-masks too wide
+    for a 12-bit tile (sweep fall-back)."""
+    from qibochem_b200 import synthetic
+
+    rng = np.random.default_rng(seed)
+    hx, hz, hc, _ = synthetic.molecular_like_hamiltonian(n, 900)
+    ex, ez = [], []
+    for w in (1, 2, 3, 3, 5, 6, 4, 13 if n >= 13 else 4, 7, 2):
+        bits = rng.choice(n, size=min(w, n), replace=False)
+        x = int(sum(1 << int(b) for b in bits))
+        for _ in range(3):
+            ex.append(x), ez.append(int(rng.integers(0, 2**n)))
+    hx = np.concatenate([hx, np.array(ex, dtype=np.uint64)])
+    hz = np.concatenate([hz, np.array(ez, dtype=np.uint64)])
+    hc = np.concatenate([hc, rng.normal(size=len(ex))])
+    return hx, hz, hc
+
+
+@pytest.mark.parametrize("n", [12, 13, 15, 16])
+def test_tiled_hpsi_matches_oracle(DeviceState, n):
+    """lambda = H psi through tiles (K6T) == the oracle's sum of Pauli applications, amplitude by amplitude, in both
+    the overwrite and the accumulate mode; <psi|lambda> == the energy of the sweep kernel."""
+    hx, hz, hc = _hpsi_inputs(n, 40 + n)
+    psi = random_state(n, 3 * n)
+    ref = np.zeros_like(psi)
+    for x, z, c in zip(hx.tolist(), hz.tolist(), hc.tolist()):
+        ref += c * O.apply_pauli(psi, int(x), int(z))
+    with DeviceState(n) as st:
+        st.from_numpy(psi)
+        st.set_option("k2_mode", 1)
+        e_sweeps = st.expectation(hx, hz, hc)
+        st.set_option("k2_mode", 2)
+        st.hpsi(hx, hz, hc)
+        ip = st.lambda_inner()
+        assert abs(np.vdot(ref, psi) - ip) < 1e-11
+        assert abs(ip.real - e_sweeps) < E_TOL
+        half = hx.size // 2
+        st.hpsi(hx[:half], hz[:half], hc[:half])
+        st.hpsi(hx[half:], hz[half:], hc[half:], accumulate=True)
+        assert abs(st.lambda_inner() - ip) < 1e-11
+        # amplitude-level check of lambda through the gradient of a one-rotation program: dE/dphi = Im<lambda|P|psi>
+        x0, z0 = int(hx[-1]), int(hz[-1])
+        grad = st.gradient_backward([x0], [z0], [0.0])
+        assert abs(grad[0] - np.vdot(ref, O.apply_pauli(psi, x0, z0)).imag) < 1e-11
+        assert np.abs(st.to_numpy() - psi).max() < AMP_TOL
+
+
+@pytest.mark.parametrize("n", [14, 16])
+def test_adjoint_gradient_through_tiles(DeviceState, n):
+    """The whole adjoint gradient with the tiled H|psi> on a UCCSD prefix + molecular-structured Hamiltonian ==
+    the parameter-shift rule evaluated with the device's own (oracle-checked) energy path on a few parameters, and
+    == the sweep-based adjoint gradient on all of them."""
+    from qibochem_b200 import synthetic
+
+    ne = 6
+    rx, rz, ra, _ = synthetic.uccsd_rotation_stream(n, ne, max_excitations=6)
+    hx, hz, hc = _hpsi_inputs(n, 50 + n)
+    hf = synthetic.hf_index(n, ne)
+    with DeviceState(n) as st:
+        def energy(angles, mode):
+            st.set_option("k2_mode", mode)
+            st.set_basis_state(hf)
+            st.apply_pauli_rotations(rx, rz, angles)
+            return st.expectation(hx, hz, hc)
+
+        grads = {}
+        for mode in (1, 2):
+            e0 = energy(ra, mode)
+            e, grads[mode] = st.energy_gradient(rx, rz, ra, hx, hz, hc)
+            assert abs(e - e0) < E_TOL
+            assert abs(st.to_numpy(offset=hf, count=1)[0] - 1.0) < AMP_TOL  # back at |HF>
+        assert np.abs(grads[1] - grads[2]).max() < 1e-11
+        for k in (0, 7, len(ra) - 1):
+            up, dn = ra.copy(), ra.copy()
+            up[k] += np.pi / 2
+            dn[k] -= np.pi / 2
+            assert abs(grads[2][k] - 0.5 * (energy(up, 1) - energy(dn, 1))) < 1e-10
