@@ -1,6 +1,7 @@
 // Shared declarations of the qibochem_b200 native library (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>  // header-only NVTX v3: ranges cost nothing unless a profiler is attached
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
@@ -41,6 +42,9 @@ struct Arena {
 };
 
 // Kernel classes for the launch counter / live profiler (qc_profile_*)
+// NVTX range names of the kernel classes (tracing), same order as KernelClass
+constexpr const char* kClassNames[] = {"qc.K0.init", "qc.K1.rotation", "qc.K2.expectation_sweep", "qc.reduce", "qc.K5.sampling",
+                                       "qc.K3.shot_statistics", "qc.K4.exchange", "qc.K2T.expectation_tiled", "qc.K6.gradient"};
 enum KernelClass { kK0Init = 0, kK1Rotation = 1, kK2Expectation = 2, kReduce = 3, kK5Sampling = 4, kK3Shots = 5, kK4Exchange = 6, kK2Tiled = 7, kGradient = 8, kNumClasses = 9 };
 
 struct TiledPlan;  // expectation_tiled.cu
@@ -146,6 +150,7 @@ struct LaunchScope {
     int cls;
     cudaEvent_t stop = nullptr;
     LaunchScope(qc_state* h_, int cls_, double algorithmic_bytes) : h(h_), cls(cls_) {
+        nvtxRangePushA(kClassNames[cls]);
         h->prof.launches[cls] += 1;
         h->prof.bytes[cls] += algorithmic_bytes;
         if (h->prof.enabled) {
@@ -157,6 +162,7 @@ struct LaunchScope {
     }
     ~LaunchScope() {
         if (stop) cudaEventRecord(stop, h->stream);
+        nvtxRangePop();
     }
 };
 

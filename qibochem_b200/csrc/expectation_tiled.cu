@@ -225,88 +225,99 @@ __device__ __forceinline__ const uint4* hop_record(const double2 (&a)[32], const
     return ep;
 }
 
-// One CTA = 2 GROUPS of 128 threads on ONE SM: two 64 KB tile buffers + the pass's blob (sub-cube headers + records,
-// <= 44 KB) in shared memory.  Both groups work on the same tile -- group 0 walks the pass's visits [0, n_rblocks0),
-// group 1 the rest (the planner balances the two lists) -- while the NEXT tile streams from HBM into the other buffer
-// (cp.async), so the tile loads of a pass hide behind the FP64 work instead of adding to it.  Everything the inner
-// loops read besides the amplitudes comes from shared memory (broadcast LDS) or the constant bank (TPass), so no
-// global-load latency sits on the critical path.
+// One CTA = 128 threads, 64 KB tile + the pass's blob (sub-cube headers + records, <= 44 KB) in shared memory;
+// 2 CTAs per SM.  Everything the inner loops read besides the amplitudes comes from shared memory (broadcast LDS)
+// or the constant bank (TPass), so no global-load latency sits on the critical path.
 // GENERIC = false: the pass holds simple quads only (the common case) and the record loop is compiled out.
-#ifndef QC_K2T_PACE
-#define QC_K2T_PACE 0  // > 0: the 32 gather loads of a visit are issued in bursts of this many (see gather_cube)
+#ifndef QC_K2T_PREFETCH
+#define QC_K2T_PREFETCH 1
+#endif
+#ifndef QC_K2T_EARLY
+#define QC_K2T_EARLY 1
 #endif
 
-__device__ __forceinline__ void issue_tile_loads(double2* __restrict__ buf, const double2* __restrict__ psi, uint64_t base,
-                                                 uint64_t off_lo, const TPass& pass) {
-    const double2* src = psi + base + off_lo;
-#pragma unroll
-    for (int k = 0; k < kTileSize / kCtaThreads; ++k) {
-        uint64_t o = 0;
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-            if (k & (1 << j)) o |= 1ull << pass.spos[8 + j];
-        cp_async16(&buf[k2_swizzle((uint32_t)k * kCtaThreads + threadIdx.x)], src + o);
-    }
-    asm volatile("cp.async.commit_group;\n" ::: "memory");
-}
-
-__device__ __forceinline__ uint64_t tile_base(uint64_t tau, uint64_t s_mask) {
-    // tile origin: deposit tau into the index bits outside S
-    uint64_t base = tau, m = s_mask;
-    while (m) {
-        const int b = __ffsll((long long)m) - 1;
-        base = insert_zero_bit(base, b);
-        m &= m - 1;
-    }
-    return base;
-}
-
 template <bool GENERIC>
-__global__ void __launch_bounds__(kCtaThreads, 1)
+__global__ void __launch_bounds__(kTileThreads, 2)
     expectation_tiled_kernel(const double2* __restrict__ psi, int n, const TPass pass, const uint4* __restrict__ units,
                              double* __restrict__ partials) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double2* tiles = reinterpret_cast<double2*>(smem_raw);
-    const uint4* blob = reinterpret_cast<const uint4*>(smem_raw + 2 * (size_t)kTileSize * sizeof(double2));
+    double2* tile = reinterpret_cast<double2*>(smem_raw);
+    const uint4* blob = reinterpret_cast<const uint4*>(smem_raw + (size_t)kTileSize * sizeof(double2));
     {
-        uint4* dst = reinterpret_cast<uint4*>(smem_raw + 2 * (size_t)kTileSize * sizeof(double2));
+        uint4* dst = reinterpret_cast<uint4*>(smem_raw + (size_t)kTileSize * sizeof(double2));
         const uint4* src = units + pass.blob_off;
-        for (uint32_t u = threadIdx.x; u < pass.blob_units; u += kCtaThreads) dst[u] = __ldg(&src[u]);
+        for (uint32_t u = threadIdx.x; u < pass.blob_units; u += kTileThreads) dst[u] = __ldg(&src[u]);
     }
-    const uint32_t tid = threadIdx.x & (kTileThreads - 1), grp = threadIdx.x >> 7;
     const uint64_t n_tiles = 1ull << (n - kTileBits);
-    // amplitude offset of tile slot t = k * 256 + threadIdx.x: the low 8 tile bits come from the thread, the high 4 from k
+    // amplitude offset of tile slot t = k * 128 + tid: the low 7 tile bits come from tid, the high 5 from k
     uint64_t off_lo = 0;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) off_lo |= (uint64_t)((threadIdx.x >> j) & 1u) << pass.spos[j];
+    for (int j = 0; j < 7; ++j) off_lo |= (uint64_t)((threadIdx.x >> j) & 1u) << pass.spos[j];
     double acc0 = 0.0, acc1 = 0.0;
-    const uint32_t rb_begin = grp ? pass.n_rblocks0 : 0u, rb_end = grp ? pass.n_rblocks : pass.n_rblocks0;
 
-    uint64_t base = 0;
-    if (blockIdx.x < n_tiles) {
-        base = tile_base(blockIdx.x, pass.s_mask);
-        issue_tile_loads(tiles, psi, base, off_lo, pass);
-    }
-    uint32_t it = 0;
-    for (uint64_t tau = blockIdx.x; tau < n_tiles; tau += gridDim.x, ++it) {
-        const double2* tile = tiles + (size_t)(it & 1u) * kTileSize;
-        cp_async_wait_all();
-        __syncthreads();  // this tile has landed for every thread; the previous tile is fully consumed (and the blob staged)
-        const uint64_t next = tau + gridDim.x;
-        uint64_t next_base = 0;
-        if (next < n_tiles) {
-            next_base = tile_base(next, pass.s_mask);
-            issue_tile_loads(tiles + (size_t)((it + 1u) & 1u) * kTileSize, psi, next_base, off_lo, pass);
+    // deposit a tile number into the index bits outside S
+    auto tile_origin = [&](uint64_t tau) {
+        uint64_t base = tau, m = pass.s_mask;
+        while (m) {
+            const int b = __ffsll((long long)m) - 1;
+            base = insert_zero_bit(base, b);
+            m &= m - 1;
         }
+        return base;
+    };
+    auto issue_tile = [&](uint64_t base) {
+        const double2* src = psi + base + off_lo;
+#pragma unroll
+        for (int k = 0; k < kTileSize / kTileThreads; ++k) {
+            uint64_t o = 0;
+#pragma unroll
+            for (int j = 0; j < 5; ++j)
+                if (k & (1 << j)) o |= 1ull << pass.spos[7 + j];
+            cp_async16(&tile[k2_swizzle((uint32_t)k * kTileThreads + threadIdx.x)], src + o);
+        }
+    };
+    // Tiles are single-buffered (two CTAs of 108 KB share an SM), so the HBM latency of a tile load has nothing of
+    // its own CTA to hide behind.  Two measures: (1) QC_K2T_PREFETCH: the tile after the next one is pulled into L2
+    // ahead of time, so that a tile's cp.async finds its sectors in L2; tile slots t and t ^ 1 are one 32-byte sector
+    // (index bit 0 is always a tile bit), so a thread touches the 16 sectors (k, tid) with k = tid mod 2.
+    // (2) QC_K2T_EARLY: the tile buffer is free as soon as the LAST visit of a tile has gathered its sub-cubes into
+    // registers; the next tile's loads are issued right there and overlap that visit's records (the planner puts the
+    // richest visit last).
+    auto prefetch_tile = [&](uint64_t base) {
+        const double2* nsrc = psi + base + off_lo;
+#pragma unroll
+        for (int k2 = 0; k2 < kTileSize / kTileThreads / 2; ++k2) {
+            const int k = 2 * k2 + (int)(threadIdx.x & 1u);
+            uint64_t o = 0;
+#pragma unroll
+            for (int j = 0; j < 5; ++j)
+                if (k & (1 << j)) o |= 1ull << pass.spos[7 + j];
+            asm volatile("prefetch.global.L2 [%0];\n" ::"l"(nsrc + o));
+        }
+    };
+    const uint64_t tile_stride = gridDim.x;
+    uint64_t base = blockIdx.x < n_tiles ? tile_origin(blockIdx.x) : 0;
+    __syncthreads();  // the blob is staged
+    if (blockIdx.x < n_tiles) issue_tile(base);
+#if QC_K2T_PREFETCH
+    if (blockIdx.x + tile_stride < n_tiles) prefetch_tile(tile_origin(blockIdx.x + tile_stride));
+#endif
+    for (uint64_t tau = blockIdx.x; tau < n_tiles; tau += tile_stride) {
+        const bool has_next = tau + tile_stride < n_tiles;
+        const uint64_t next_base = has_next ? tile_origin(tau + tile_stride) : 0;
+#if QC_K2T_PREFETCH
+        if (tau + 2 * tile_stride < n_tiles) prefetch_tile(tile_origin(tau + 2 * tile_stride));
+#endif
+        cp_async_wait_all();
+        __syncthreads();  // the tile has landed for every thread
 
-        for (uint32_t rb = rb_begin; rb < rb_end; ++rb) {
+        for (uint32_t rb = 0; rb < pass.n_rblocks; ++rb) {
             const uint4 b0 = blob[rb * kRBlockUnits];      // sbit[0..4], quad_mask
             const uint4 b1 = blob[rb * kRBlockUnits + 1];  // rec_off, n_recs, n_groups, hop_mask
             // tile-local origin of this thread's sub-cube (and its swizzled slot) from the visit's two origin tables
             const uint32_t* otab = reinterpret_cast<const uint32_t*>(blob + rb * kRBlockUnits + 2);
-            const uint32_t packed = otab[tid & 15u] ^ otab[16u + (tid >> 4)];
-            const uint32_t org = packed >> 16;
-            uint32_t org_sw = packed & 0xffffu;
+            const uint32_t packed = otab[threadIdx.x & 15u] ^ otab[16u + (threadIdx.x >> 4)];
+            const uint32_t org = packed >> 16, org_sw = packed & 0xffffu;
             const uint32_t sb0 = b0.x & 0xffffu, sb1 = b0.x >> 16, sb2 = b0.y & 0xffffu, sb3 = b0.y >> 16, sb4 = b0.z & 0xffffu;
             double2 a[32];
 #pragma unroll
@@ -318,14 +329,17 @@ __global__ void __launch_bounds__(kCtaThreads, 1)
                 if (p & 8) off ^= sb3;
                 if (p & 16) off ^= sb4;
                 a[p] = tile[off];
-#if QC_K2T_PACE > 0
-                // pacing: the address of the next burst depends on the data of this one, so a warp never has more than
-                // QC_K2T_PACE gather loads queued and the other group's table loads are not stuck behind 32 of them
-                if ((p % QC_K2T_PACE) == QC_K2T_PACE - 1 && p != 31) org_sw ^= (uint32_t)__double2hiint(a[p].x) & pass.zero;
-#endif
             }
+#if QC_K2T_EARLY
+            if (rb + 1 == pass.n_rblocks) {
+                // last visit of the tile: once the whole CTA has passed this barrier every sub-cube has been read
+                // (__syncthreads orders the shared-memory reads above before the writes of the copies below)
+                __syncthreads();
+                if (has_next) issue_tile(next_base);
+            }
+#endif
             const uint4* rp = blob + b1.x;
-            const uint32_t rho8 = ((tid >> 6) & 1u) * 8u;  // two-table records: units to skip for rho = 1
+            const uint32_t rho8 = ((threadIdx.x >> 6) & 1u) * 8u;  // two-table records: units to skip for rho = 1
             // ---- simple quads of this cube (coordinate vectors of weight 4 and 3): straight-line code, no dispatch
             const uint32_t quad_mask = b0.z >> 16;
             // software-pipelined: a slot leaves its four partial sums and its sign pending and the next slot folds
@@ -352,7 +366,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1)
 #undef QC_QUAD
             // ---- HOP records (weight-2 x-masks): straight-line code per coordinate vector
             if (GENERIC && b1.w) {
-                const uint32_t hop_mask = b1.w, rho = (tid >> 6) & 1u;
+                const uint32_t hop_mask = b1.w, rho = (threadIdx.x >> 6) & 1u;
 #define QC_HOP(S, XR) \
     if (hop_mask & (1u << S)) rp = hop_record<XR>(a, rp, base, org, rho, acc0, acc1);
                 QC_HOP(0, 1) QC_HOP(1, 2) QC_HOP(2, 4) QC_HOP(3, 8) QC_HOP(4, 16)
@@ -405,10 +419,19 @@ __global__ void __launch_bounds__(kCtaThreads, 1)
                 }
             }
         }
+#if !QC_K2T_EARLY
+        __syncthreads();  // tile fully consumed
+        if (has_next) issue_tile(next_base);
+#else
+        if (pass.n_rblocks == 0) {
+            __syncthreads();
+            if (has_next) issue_tile(next_base);
+        }
+#endif
         base = next_base;
     }
-    // CTA reduction (256 threads), fixed order => deterministic
-    __shared__ double wpart[kCtaThreads / 32];
+    // CTA reduction (kTileThreads = 128 threads), fixed order => deterministic
+    __shared__ double wpart[kTileThreads / 32];
     double acc = warp_sum(acc0 + acc1);
     __syncthreads();
     if ((threadIdx.x & 31) == 0) wpart[threadIdx.x >> 5] = acc;
@@ -416,7 +439,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1)
     if (threadIdx.x == 0) {
         double t = 0.0;
 #pragma unroll
-        for (int k = 0; k < kCtaThreads / 32; ++k) t += wpart[k];
+        for (int k = 0; k < kTileThreads / 32; ++k) t += wpart[k];
         partials[blockIdx.x] = t;
     }
 }
@@ -485,8 +508,8 @@ int run_tiled_expectation(qc_state* h, size_t T, const uint64_t* xs, const uint6
     h->k2plans.push_back(found);  // most recently used last
     const TiledPlan* plan = found;
     const HostPlan* hp = plan->host;
-    const size_t smem = 2 * (size_t)kTileSize * sizeof(double2) + (size_t)kBlobCapUnits * 16;
-    const int ctas = 1;  // one CTA of two 128-thread groups per SM
+    const size_t smem = (size_t)kTileSize * sizeof(double2) + (size_t)kBlobCapUnits * 16;
+    const int ctas = 2;
     for (auto kernel : {expectation_tiled_kernel<true>, expectation_tiled_kernel<false>}) {
         QC_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         QC_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -503,7 +526,7 @@ int run_tiled_expectation(qc_state* h, size_t T, const uint64_t* xs, const uint6
             LaunchScope ls(h, kK2Tiled, 16.0 * (double)h->dim * (double)pass.n_groups);
             h->h2d_bytes += sizeof(TPass);
             auto kernel = pass.n_generic ? expectation_tiled_kernel<true> : expectation_tiled_kernel<false>;
-            kernel<<<nb, kCtaThreads, smem, h->stream>>>(h->psi, h->n, pass, plan->d_units, h->d_partials + p * nb);
+            kernel<<<nb, kTileThreads, smem, h->stream>>>(h->psi, h->n, pass, plan->d_units, h->d_partials + p * nb);
         }
         QC_CHECK(cudaGetLastError());
     }

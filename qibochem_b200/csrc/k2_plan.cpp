@@ -573,33 +573,17 @@ HostPlan* build_host_plan(int n, size_t T, const uint64_t* xs, const uint64_t* z
             pass.n_rblocks = (uint32_t)cur.size();
             pass.n_groups = cur_groups;
             {
-                // The CTA's two thread groups each walk one list of visits: longest-processing-time split by the
-                // per-visit cost model fitted to the kernel (~495 clk per gather, ~154 per quad record,
-                // ~1030 per HOP record, generic records by their size), group 0's visits first.
-                std::vector<std::pair<uint32_t, size_t>> cost(cur.size());
+                // The kernel issues the NEXT tile's loads right after the gather of a tile's LAST visit, so that they
+                // overlap that visit's records: the visit with the most record work goes last.
+                size_t richest = 0;
+                uint32_t best = 0;
                 for (size_t i = 0; i < cur.size(); ++i) {
-                    uint32_t c = 495;
-                    for (int j = 0; j < kQuadSlots; ++j) c += cur[i].quads[j].empty() ? 0u : 154u;
-                    for (int j = 0; j < kHopSlots; ++j) c += cur[i].hops[j].empty() ? 0u : 700u + 12u * (uint32_t)cur[i].hops[j].size();
-                    c += 12u * (uint32_t)cur[i].recs.size();
-                    cost[i] = {c, i};
+                    uint32_t c = (uint32_t)cur[i].recs.size();
+                    for (int j = 0; j < kQuadSlots; ++j) c += (uint32_t)cur[i].quads[j].size();
+                    for (int j = 0; j < kHopSlots; ++j) c += (uint32_t)cur[i].hops[j].size();
+                    if (c >= best) best = c, richest = i;
                 }
-                std::stable_sort(cost.begin(), cost.end(), [](const auto& a, const auto& b) { return a.first > b.first; });
-                uint64_t load[2] = {0, 0};
-                std::vector<size_t> bin[2];
-                for (const auto& ci : cost) {
-                    const int g = load[1] < load[0] ? 1 : 0;
-                    load[g] += ci.first;
-                    bin[g].push_back(ci.second);
-                }
-                std::vector<RB> ordered;
-                ordered.reserve(cur.size());
-                for (int g = 0; g < 2; ++g) {
-                    std::sort(bin[g].begin(), bin[g].end());  // keep the planner's visit order inside a group
-                    for (size_t i : bin[g]) ordered.push_back(std::move(cur[i]));
-                }
-                pass.n_rblocks0 = (uint32_t)bin[0].size();
-                cur.swap(ordered);
+                if (richest + 1 != cur.size()) std::swap(cur[richest], cur.back());
             }
             uint32_t rec_off = (uint32_t)cur.size() * kRBlockUnits;
             for (RB& rb : cur) {

@@ -18,9 +18,7 @@ namespace qc {
 constexpr int kTileBits = 12;                       // amplitudes of one tile: 4096 (64 KB of shared memory)
 constexpr int kTileSize = 1 << kTileBits;
 constexpr int kRBits = 5;                           // register sub-cube: 32 amplitudes per thread
-constexpr int kTileThreads = kTileSize >> kRBits;   // 128: one thread per sub-cube of a visit
-constexpr int kGroups = 2;                          // thread groups of a CTA; each walks its own list of visits
-constexpr int kCtaThreads = kTileThreads * kGroups; // 256
+constexpr int kTileThreads = kTileSize >> kRBits;   // 128
 constexpr int kPairsPerCube = 16;                   // pairs {p, p^x} of a sub-cube
 constexpr int kSlots = 4;                           // pattern sums A[0..3] shared by the LIN entries of a group
 
@@ -30,7 +28,7 @@ QC_HD inline uint32_t k2_swizzle(uint32_t t) { return t ^ ((t >> 3) & 7u) ^ ((t 
 
 // Per-pass "blob": [TRBlock headers][record stream], staged ONCE per CTA into shared memory next to the tile, so
 // that walking the records costs broadcast LDS instead of dependent global loads.
-constexpr uint32_t kBlobCapUnits = 2816;            // 44 KB of 16-byte units per pass (2 tile buffers of 64 KB + blob: 172 KB)
+constexpr uint32_t kBlobCapUnits = 2816;            // 44 KB of 16-byte units per pass (tile 64 KB + blob: 2 CTAs/SM)
 
 struct TPass {             // kernel parameter (constant bank)
     uint64_t s_mask;       // the kTileBits index bits of the tile (always contains bit 0)
@@ -40,8 +38,6 @@ struct TPass {             // kernel parameter (constant bank)
     uint32_t n_rblocks;
     uint32_t n_groups;     // x-masks served by this pass
     uint32_t n_generic;    // records outside the straight-line quad path (0: the lean kernel variant runs the pass)
-    uint32_t n_rblocks0;   // visits [0, n_rblocks0) belong to thread group 0, the rest to group 1 (balanced by cost)
-    uint32_t zero;         // always 0 (an opaque zero for the kernel's paced gather)
     uint32_t pad;
 };
 

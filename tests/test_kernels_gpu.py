@@ -116,9 +116,15 @@ def test_ucc_double_is_one_pass_and_matches_gate_path(DeviceState):
             x, z = O.pauli_masks(n, string)
             xs.append(x), zs.append(z), phis.append((2j * coeff * th).real)
     with DeviceState(n) as st:
+        st.set_option("k1_mode", 1)
         st.set_basis_state(((1 << ne) - 1) << (n - ne))
         passes = st.apply_pauli_rotations(xs, zs, phis)
         assert passes == 2  # 8 strings of the double -> 1 pass, 2 strings of the single -> 1 pass
+        assert np.abs(st.to_numpy() - ref).max() < AMP_TOL
+        # default mode on a small register (n <= 13): the whole program is ONE launch with the state in shared memory
+        st.set_option("k1_mode", 0)
+        st.set_basis_state(((1 << ne) - 1) << (n - ne))
+        assert st.apply_pauli_rotations(xs, zs, phis) == 1
         assert np.abs(st.to_numpy() - ref).max() < AMP_TOL
 
 
