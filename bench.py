@@ -55,6 +55,8 @@ def parse_args():
     ap.add_argument("--cpu-sample-qubits", type=int, default=24)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity-check", action="store_true", help="N > 1: skip the oracle / 1-GPU-twin parity checks")
+    ap.add_argument("--no-ladder-point", action="store_true", help="skip the 32-qubit single-GPU point of the weak-scaling ladder")
+    ap.add_argument("--no-small-configs", action="store_true", help="skip BASELINE configs 1-3 (4 / 12 / 14 qubits)")
     ap.add_argument("--no-full-stream", action="store_true", help="skip the extra full-UCCSD-stream measurement")
     return ap.parse_args()
 
@@ -359,6 +361,11 @@ def main():
     if not args.no_cpu_baseline:
         cpu = cpu_reference_sample(wl, args.cpu_sample_qubits)
         cpu["fit"] = cpu_scaling_points()
+    small = None if args.no_small_configs else measure_small_configs()
+    ladder = None
+    if not args.no_ladder_point and n == 30 and args.rotations == 1024 and torch.cuda.get_device_properties(0).total_memory > 100e9:
+        st.close()
+        ladder = measure_ladder_point(32, args, stream)
     line = {
         "metric": METRIC, "value": value * 2.0 ** (n - 30), "unit": unit_for(n), "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -367,7 +374,7 @@ def main():
         "passes_per_step": {"k1_rotation_passes": passes, "k2_xmask_sweeps": sweeps},
         "wall_ms_per_step": 1e3 * wall / args.steps,
         "clocks": clock_info, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
-        "full_uccsd_stream": full,
+        "full_uccsd_stream": full, "small_configs": small, "weak_ladder_32q_1gpu": ladder,
     }  # fmt: skip
     out.emit(line)
 
@@ -430,6 +437,105 @@ def build_roofline(wl, prof, args, dev_ms):
         "peak_source": hbm_src, "note": "achieved = algorithmic bytes / device time", "traffic": None,
         "hbm_actual": {"GBps": hbm_actual_gbps}, "algorithmic_bytes_per_launch": d["bytes"] / max(d["launches"], 1),
     }  # fmt: skip
+
+
+def measure_ladder_point(n: int, args, stream) -> dict:
+    """SURVEY 7's weak-scaling ladder is 32 q @ 1, 33 q @ 2, 34 q @ 4, 35 q @ 8 (2^32 amplitudes per GPU): the 1-GPU
+    point, with the SAME generators as the N > 1 arms (the n-qubit Hamiltonian has more hopping strings per x-mask than
+    the 30-qubit one, so per-x-mask costs across the ladder compare like with like).  One warm-up + one timed step."""
+    import torch
+
+    from qibochem_b200.engine import DeviceState
+
+    nelec = 2 * ((n * 14 // 30) // 2)
+    wl = workload(n, nelec, args.rotations, args.terms)
+    with DeviceState(n, device=0, stream=stream.cuda_stream) as st:
+        ms = e = None
+        for _ in range(2):
+            st.profile_reset()
+            st.profile_enable(True)
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record(stream)
+            st.set_basis_state(wl["hf"])
+            st.apply_pauli_rotations(wl["rx"], wl["rz"], wl["ra"])
+            e = wl["const"] + st.expectation(wl["hx"], wl["hz"], wl["hc"])
+            ev1.record(stream)
+            torch.cuda.synchronize()
+            ms = ev0.elapsed_time(ev1)
+            prof = st.profile()
+        passes = st.last_sweeps
+    k2 = prof["k2_tiled"]["ms"]
+    return {"qubits": n, "ms_per_step": ms, "thirty_qubit_equivalent_evals_per_sec": 2.0 ** (n - 30) * 1e3 / ms, "energy": e,
+            "x_masks": wl["n_xmasks"], "k2_tiled_ms": k2, "k2_passes": int(passes),
+            "k2_ms_per_xmask_per_2^32_amplitudes": k2 / wl["n_xmasks"] * 2.0 ** (32 - n), "k1_ms": prof["k1_rotation"]["ms"]}  # fmt: skip
+
+
+def measure_small_configs() -> dict:
+    """BASELINE configs 1-3 (the launch-bound regime) through the public API, bounded to a few seconds:
+    H2 (4 q, doc fixture) and LiH-shaped (12 q) exact energies per `set_parameters` + `hamiltonian.expectation`, and the
+    BeH2-shaped (14 q) QWC-grouped sampled energy at 10^6 shots per group (`expectation_from_samples`).  LiH / BeH2 use
+    molecule-SHAPED synthetic integrals (no PySCF in the image): sizes and term structure are the molecule's."""
+    from qibochem_b200.ansatz import circuit_ansatz
+    from qibochem_b200.measurement import expectation_from_samples
+    from qibochem_b200.measurement.optimization import _measurement_basis_rotations
+    from qibochem_b200.runtime import get_runtime
+    from tests.fixtures import h2_molecule, synthetic_molecule
+
+    out = {}
+    for key, mol in (("h2_4q", h2_molecule()), ("lih_shaped_12q", synthetic_molecule(6, 4, 1))):
+        ham = mol.hamiltonian()
+        circuit = circuit_ansatz(mol, "ucc")
+        params = np.array([complex(p[0]).real for p in circuit.get_parameters()], dtype=float)
+        e = ham.expectation(circuit)  # warm-up: compiles the program
+        reps = 100
+        t0 = time.perf_counter()
+        for k in range(reps):
+            circuit.set_parameters(params * (1.0 + 1e-3 * k))
+            e = ham.expectation(circuit)
+        dt = (time.perf_counter() - t0) / reps
+        st = get_runtime().state(mol.nso)
+        st.profile_reset()
+        st.profile_enable(True)
+        circuit.set_parameters(params)
+        e = ham.expectation(circuit)
+        prof = st.profile()
+        st.profile_enable(False)
+        out[key] = {"qubits": mol.nso, "rotations": int(params.size), "terms": int(ham.nterms), "energy": e,
+                    "us_per_energy_e2e": 1e6 * dt, "energies_per_sec": 1.0 / dt,
+                    "device_us": {k: round(1e3 * v["ms"], 2) for k, v in prof.items() if v["launches"]},
+                    "launches_per_energy": int(sum(v["launches"] for v in prof.values()))}  # fmt: skip
+    mol = synthetic_molecule(7, 6, 3)
+    ham = mol.hamiltonian()
+    circuit = circuit_ansatz(mol, "ucc", thetas=np.random.default_rng(4).uniform(-0.1, 0.1, size=204))
+    t0 = time.perf_counter()
+    groups = _measurement_basis_rotations(ham, "qwc")
+    t_group = time.perf_counter() - t0
+    exact = ham.expectation(circuit)
+    shots = 1_000_000
+    st = get_runtime().state(mol.nso)
+    e = dt = None
+    for rep in range(2):
+        st.profile_reset()
+        st.profile_enable(True)
+        t0 = time.perf_counter()
+        e = expectation_from_samples(circuit, ham, n_shots=shots, grouping="qwc", seed=5 + rep)
+        dt = time.perf_counter() - t0
+    prof = st.profile()
+    st.profile_enable(False)
+    n_masks = int(ham.nterms)
+    out["beh2_shaped_14q_sampled"] = {
+        "qubits": mol.nso, "rotations": len(circuit.get_parameters()), "terms": n_masks, "qwc_groups": len(groups),
+        "shots_per_group": shots, "s_per_sampled_energy": dt, "Gshots_per_sec": len(groups) * shots / dt / 1e9,
+        "exact": exact, "sampled": e, "abs_diff": abs(e - exact), "grouping_s": t_group,
+        "device_ms": {k: round(v["ms"], 2) for k, v in prof.items() if v["launches"]},
+        # rooflines of the two sampling-path kernels (per group: one K5 draw of `shots` shots, one K3 pass over them)
+        "k3_parity_sums": {"algorithmic_GBps": (prof["k3_shots"]["bytes"] / 1e9 / (prof["k3_shots"]["ms"] / 1e3)) if prof["k3_shots"]["ms"] else None,
+                           "note": "8 B per shot and mask tile (uint64 samples), integer ALU / L2 bound: the samples of a group (8 MB) stay in L2"},
+        "k5_sampling": {"ms": prof["k5_sampling"]["ms"], "shots_per_sec": len(groups) * shots / (prof["k5_sampling"]["ms"] / 1e3) if prof["k5_sampling"]["ms"] else None,
+                        "note": "one warp per shot: Philox + binary search over chunk prefix sums + scan inside a 128-amplitude chunk; latency bound (L2)"},
+    }  # fmt: skip
+    get_runtime().release_states()
+    return out
 
 
 def measure_full_stream(wl, st, stream):

@@ -213,6 +213,8 @@ def main_sharded(args, n: int, nelec: int, out) -> None:
             },
             "exchange": {"global_bit_swaps_per_step": swaps / args.steps, "bytes_out_per_gpu_per_swap": local.dim * 8,
                          "nvlink_GBps_per_direction_incl_barriers": nvlink, "nvlink_peak_GBps": 770.0},
+            "k2_ms_per_xmask_per_2^32_amplitudes_rank0": (prof["k2_tiled"]["ms"] / args.steps / wl["n_xmasks"] * 2.0 ** (32 - (n - g))) if prof["k2_tiled"]["ms"] else None,
+            "k2_passes_per_step": st.last_sweeps,
             "cpu_baseline": None,
             "parity_check": parity,
             "full_uccsd_stream": full,

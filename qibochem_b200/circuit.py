@@ -24,7 +24,7 @@ from qibochem_b200.runtime import get_runtime
 class Program:
     """Compiled form of a circuit (everything the device needs)."""
 
-    __slots__ = ("nqubits", "basis_index", "xmask", "zmask", "angle", "param_rot", "param_scale", "param_owner", "phase",
+    __slots__ = ("nqubits", "basis_index", "xmask", "zmask", "angle", "param_rot", "param_scale", "param_owner", "n_param_gates", "phase",
                  "measured", "x_basis_mask", "y_basis_mask")  # fmt: skip
 
 
@@ -38,8 +38,28 @@ class Circuit:
             get_runtime().configure_accelerators(kwargs["accelerators"])
         self.nqubits = int(nqubits)
         self.init_kwargs = dict(kwargs)
-        self.queue: list[_gates.Gate] = []
+        self._queue: list[_gates.Gate] = []
         self._program: Program | None = None
+        self._pending: np.ndarray | None = None  # parameters set through the fast path, not yet written to the gates
+
+    @property
+    def queue(self) -> list[_gates.Gate]:
+        """The gate list (qibo's ``circuit.queue``).  Parameters that an optimiser loop pushed through the fast path of
+        ``set_parameters`` are written back to the gate objects first."""
+        self._sync_gates()
+        return self._queue
+
+    @queue.setter
+    def queue(self, gates) -> None:
+        self._queue = list(gates)
+        self._pending = None
+        self._program = None
+
+    def _sync_gates(self) -> None:
+        if self._pending is not None:
+            flat, self._pending = self._pending, None
+            for g, p in zip((g for g in self._queue if g.n_params), flat.tolist()):
+                g.parameters = (p,)
 
     # ---- building ---------------------------------------------------------------------------------------------
     def add(self, gate) -> None:
@@ -96,10 +116,22 @@ class Circuit:
     # ---- parameters -------------------------------------------------------------------------------------------
     def get_parameters(self) -> list[tuple]:
         """One 1-tuple per parametrized gate, in queue order (qibo's default ``format="list"``)."""
+        if self._pending is not None:
+            return [(p,) for p in self._pending.tolist()]
         return [tuple(g.parameters) for g in self.parametrized_gates]
 
     def set_parameters(self, parameters) -> None:
         """Flat sequence with one value per parametrized gate (or a list of 1-tuples as ``get_parameters`` gives)."""
+        if self._program is not None and isinstance(parameters, np.ndarray) and parameters.ndim == 1 and parameters.dtype.kind in "fiu":
+            # fast path of an optimiser loop (README.md:45 of the reference calls this once per energy): only the angle
+            # vector of the compiled program changes; the gate objects are updated lazily (see `queue`)
+            prog = self._program
+            if parameters.size != prog.n_param_gates:
+                raise ValueError(f"Given list of parameters has length {parameters.size} while the circuit contains {prog.n_param_gates} parametrized gates.")
+            flat = parameters.astype(np.float64)  # a copy: the caller may reuse its array
+            prog.angle[prog.param_rot] = prog.param_scale * flat[prog.param_owner]
+            self._pending = flat
+            return
         pg = self.parametrized_gates
         params = list(parameters)
         if len(params) != len(pg):
@@ -160,6 +192,7 @@ class Circuit:
         prog.param_rot = np.array(prot, dtype=np.int64)
         prog.param_scale = np.array(pscale, dtype=np.float64)
         prog.param_owner = np.array(powner, dtype=np.int64)  # index into parametrized_gates / get_parameters()
+        prog.n_param_gates = n_param_gates
         prog.phase = phase
         prog.measured = measured
         prog.x_basis_mask = sum(1 << (n - 1 - q) for q, b in measured if b == "X")

@@ -51,6 +51,8 @@ struct TiledPlan;  // expectation_tiled.cu
 void free_tiled_plan(TiledPlan* p);
 struct HpPlan;     // gradient_tiled.cu
 void free_hp_plan(HpPlan* p);
+struct SweepPlan;  // expectation.cu
+void free_sweep_plan(SweepPlan* p);
 
 struct Profiler {
     bool enabled = false;
@@ -91,6 +93,7 @@ struct qc_state {
     qc::Profiler prof;
     uint64_t h2d_bytes = 0, d2h_bytes = 0;  // host<->device bytes moved by the product path since the last reset
     std::vector<qc::TiledPlan*> k2plans;  // cached plans of the tiled expectation (keyed by a hash of the term list; LRU)
+    qc::SweepPlan* sweep_plan = nullptr;  // grouped device program of the last term list the sweep kernel ran
     qc::HpPlan* hp_plan = nullptr;        // cached plan of the tiled H|psi> (adjoint gradient), last term list only
     int k1_mode = 0;                  // 0 auto, 1 one HBM pass per fused run, 2 shared-memory tiles whenever a run fits
     int k2_mode = 0;                  // 0 auto, 1 force sweeps (one HBM pass per x-mask), 2 force tiles

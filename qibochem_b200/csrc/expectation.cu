@@ -134,58 +134,91 @@ __global__ void __launch_bounds__(kThreads) expectation_kernel(const double2* __
     if (threadIdx.x == 0) partials[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = t;
 }
 
+// Grouped device program of a term list, kept on the handle between calls: an optimiser loop evaluates the SAME
+// Hamiltonian thousands of times, and for a small register the per-call sort + upload cost more than the kernels.
+struct SweepPlan {
+    std::vector<uint64_t> key_x, key_z;
+    std::vector<double> key_c;
+    bool per_term = false;
+    XGroup* d_groups = nullptr;
+    TermDev* d_terms = nullptr;
+    size_t ng = 0;
+    ~SweepPlan() {
+        if (d_groups) cudaFree(d_groups);
+        if (d_terms) cudaFree(d_terms);
+    }
+    bool matches(size_t T, const uint64_t* xs, const uint64_t* zs, const double* cs, bool pt) const {
+        return per_term == pt && key_x.size() == T && memcmp(key_x.data(), xs, T * 8) == 0 &&
+               memcmp(key_z.data(), zs, T * 8) == 0 && (pt || memcmp(key_c.data(), cs, T * 8) == 0);
+    }
+};
+void free_sweep_plan(SweepPlan* p) { delete p; }
+
 // Sweep path: one launch row per x-group.  Total -> h->d_out[out_slot]; per-group values -> h->d_out[out_slot+1 ...].
 static int run_sweeps(qc_state* h, size_t T, const uint64_t* xmask, const uint64_t* zmask, const double* coeff,
                       bool per_term, size_t out_slot, size_t* ng_out) {
-    // ---- group the terms by x-mask (stable), even-nY terms first inside a group
-    std::vector<uint32_t> order(T);
-    std::iota(order.begin(), order.end(), 0u);
-    if (!per_term) {
-        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
-            if (xmask[a] != xmask[b]) return xmask[a] < xmask[b];
-            const int oa = __builtin_popcountll(xmask[a] & zmask[a]) & 1, ob = __builtin_popcountll(xmask[b] & zmask[b]) & 1;
-            return oa < ob;
-        });
-    }
-    std::vector<XGroup> groups;
-    std::vector<TermDev> tdev(T);
-    for (size_t k = 0; k < T; ++k) {
-        const uint32_t t = order[k];
-        const int ny = __builtin_popcountll(xmask[t] & zmask[t]);
-        const double sg = ((ny >> 1) & 1) ? -1.0 : 1.0;
-        tdev[k].z = zmask[t];
-        tdev[k].d = (per_term ? 1.0 : coeff[t]) * sg;
-        const bool new_group = per_term || groups.empty() || groups.back().x != xmask[t] ||
-                               groups.back().n_even + groups.back().n_odd >= (uint32_t)kMaxGroupTerms;
-        if (new_group) {
-            XGroup g;
-            g.x = xmask[t];
-            g.hb = g.x ? 63 - __builtin_clzll(g.x) : -1;
-            g.first = (uint32_t)k;
-            g.n_even = g.n_odd = 0;
-            groups.push_back(g);
+    SweepPlan* sp = h->sweep_plan;
+    if (!(sp && sp->matches(T, xmask, zmask, coeff, per_term))) {
+        // ---- group the terms by x-mask (stable), even-nY terms first inside a group
+        std::vector<uint32_t> order(T);
+        std::iota(order.begin(), order.end(), 0u);
+        if (!per_term) {
+            std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+                if (xmask[a] != xmask[b]) return xmask[a] < xmask[b];
+                const int oa = __builtin_popcountll(xmask[a] & zmask[a]) & 1, ob = __builtin_popcountll(xmask[b] & zmask[b]) & 1;
+                return oa < ob;
+            });
         }
-        if (ny & 1) {
-            ++groups.back().n_odd;
-        } else {
-            // a group split at kMaxGroupTerms keeps "even first" because the sort put all evens before odds
-            QC_REQUIRE(groups.back().n_odd == 0, "internal: term order inside an x-group");
-            ++groups.back().n_even;
+        std::vector<XGroup> groups;
+        std::vector<TermDev> tdev(T);
+        for (size_t k = 0; k < T; ++k) {
+            const uint32_t t = order[k];
+            const int ny = __builtin_popcountll(xmask[t] & zmask[t]);
+            const double sg = ((ny >> 1) & 1) ? -1.0 : 1.0;
+            tdev[k].z = zmask[t];
+            tdev[k].d = (per_term ? 1.0 : coeff[t]) * sg;
+            const bool new_group = per_term || groups.empty() || groups.back().x != xmask[t] ||
+                                   groups.back().n_even + groups.back().n_odd >= (uint32_t)kMaxGroupTerms;
+            if (new_group) {
+                XGroup g;
+                g.x = xmask[t];
+                g.hb = g.x ? 63 - __builtin_clzll(g.x) : -1;
+                g.first = (uint32_t)k;
+                g.n_even = g.n_odd = 0;
+                groups.push_back(g);
+            }
+            if (ny & 1) {
+                ++groups.back().n_odd;
+            } else {
+                // a group split at kMaxGroupTerms keeps "even first" because the sort put all evens before odds
+                QC_REQUIRE(groups.back().n_odd == 0, "internal: term order inside an x-group");
+                ++groups.back().n_even;
+            }
         }
+        // ---- ship the program (kept on the device until a different term list arrives)
+        QC_CHECK(cudaStreamSynchronize(h->stream));  // the old program may still be read by in-flight sweeps
+        delete h->sweep_plan;
+        h->sweep_plan = nullptr;
+        sp = new SweepPlan();
+        sp->per_term = per_term;
+        sp->ng = groups.size();
+        if (cudaMalloc(&sp->d_groups, groups.size() * sizeof(XGroup)) != cudaSuccess ||
+            cudaMalloc(&sp->d_terms, T * sizeof(TermDev)) != cudaSuccess ||
+            cudaMemcpy(sp->d_groups, groups.data(), groups.size() * sizeof(XGroup), cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaMemcpy(sp->d_terms, tdev.data(), T * sizeof(TermDev), cudaMemcpyHostToDevice) != cudaSuccess) {
+            delete sp;
+            set_error("qc_expectation: could not upload the sweep program");
+            return 1;
+        }
+        h->h2d_bytes += groups.size() * sizeof(XGroup) + T * sizeof(TermDev);
+        sp->key_x.assign(xmask, xmask + T);
+        sp->key_z.assign(zmask, zmask + T);
+        if (!per_term) sp->key_c.assign(coeff, coeff + T);
+        h->sweep_plan = sp;
     }
-    const size_t ng = groups.size();
-
-    // ---- ship the program
-    const size_t bytes_groups = ng * sizeof(XGroup), bytes_terms = T * sizeof(TermDev);
-    const size_t off_terms = (bytes_groups + 255) & ~(size_t)255;
-    QC_CHECK(cudaStreamSynchronize(h->stream));
-    if (h->arena.ensure(off_terms + bytes_terms)) return 1;
-    memcpy(h->arena.host, groups.data(), bytes_groups);
-    memcpy((char*)h->arena.host + off_terms, tdev.data(), bytes_terms);
-    QC_CHECK(cudaMemcpyAsync(h->arena.dev, h->arena.host, off_terms + bytes_terms, cudaMemcpyHostToDevice, h->stream));
-    h->h2d_bytes += off_terms + bytes_terms;
-    const XGroup* dgroups = (const XGroup*)h->arena.dev;
-    const TermDev* dterms = (const TermDev*)((char*)h->arena.dev + off_terms);
+    const size_t ng = sp->ng;
+    const XGroup* dgroups = sp->d_groups;
+    const TermDev* dterms = sp->d_terms;
 
     const int nbx = grid_for(h->dim >> 1, 4, h->sm_count);
     const size_t chunk = std::min(ng, (size_t)kMaxGroupsPerLaunch);

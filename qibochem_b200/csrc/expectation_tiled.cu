@@ -229,13 +229,6 @@ __device__ __forceinline__ const uint4* hop_record(const double2 (&a)[32], const
 // 2 CTAs per SM.  Everything the inner loops read besides the amplitudes comes from shared memory (broadcast LDS)
 // or the constant bank (TPass), so no global-load latency sits on the critical path.
 // GENERIC = false: the pass holds simple quads only (the common case) and the record loop is compiled out.
-#ifndef QC_K2T_PREFETCH
-#define QC_K2T_PREFETCH 1
-#endif
-#ifndef QC_K2T_EARLY
-#define QC_K2T_EARLY 1
-#endif
-
 template <bool GENERIC>
 __global__ void __launch_bounds__(kTileThreads, 2)
     expectation_tiled_kernel(const double2* __restrict__ psi, int n, const TPass pass, const uint4* __restrict__ units,
@@ -255,17 +248,18 @@ __global__ void __launch_bounds__(kTileThreads, 2)
     for (int j = 0; j < 7; ++j) off_lo |= (uint64_t)((threadIdx.x >> j) & 1u) << pass.spos[j];
     double acc0 = 0.0, acc1 = 0.0;
 
-    // deposit a tile number into the index bits outside S
-    auto tile_origin = [&](uint64_t tau) {
-        uint64_t base = tau, m = pass.s_mask;
-        while (m) {
-            const int b = __ffsll((long long)m) - 1;
-            base = insert_zero_bit(base, b);
-            m &= m - 1;
+    for (uint64_t tau = blockIdx.x; tau < n_tiles; tau += gridDim.x) {
+        // tile origin: deposit tau into the index bits outside S
+        uint64_t base = tau;
+        {
+            uint64_t m = pass.s_mask;
+            while (m) {
+                const int b = __ffsll((long long)m) - 1;
+                base = insert_zero_bit(base, b);
+                m &= m - 1;
+            }
         }
-        return base;
-    };
-    auto issue_tile = [&](uint64_t base) {
+        __syncthreads();  // previous tile fully consumed (and, the first time, the blob staged)
         const double2* src = psi + base + off_lo;
 #pragma unroll
         for (int k = 0; k < kTileSize / kTileThreads; ++k) {
@@ -275,41 +269,8 @@ __global__ void __launch_bounds__(kTileThreads, 2)
                 if (k & (1 << j)) o |= 1ull << pass.spos[7 + j];
             cp_async16(&tile[k2_swizzle((uint32_t)k * kTileThreads + threadIdx.x)], src + o);
         }
-    };
-    // Tiles are single-buffered (two CTAs of 108 KB share an SM), so the HBM latency of a tile load has nothing of
-    // its own CTA to hide behind.  Two measures: (1) QC_K2T_PREFETCH: the tile after the next one is pulled into L2
-    // ahead of time, so that a tile's cp.async finds its sectors in L2; tile slots t and t ^ 1 are one 32-byte sector
-    // (index bit 0 is always a tile bit), so a thread touches the 16 sectors (k, tid) with k = tid mod 2.
-    // (2) QC_K2T_EARLY: the tile buffer is free as soon as the LAST visit of a tile has gathered its sub-cubes into
-    // registers; the next tile's loads are issued right there and overlap that visit's records (the planner puts the
-    // richest visit last).
-    auto prefetch_tile = [&](uint64_t base) {
-        const double2* nsrc = psi + base + off_lo;
-#pragma unroll
-        for (int k2 = 0; k2 < kTileSize / kTileThreads / 2; ++k2) {
-            const int k = 2 * k2 + (int)(threadIdx.x & 1u);
-            uint64_t o = 0;
-#pragma unroll
-            for (int j = 0; j < 5; ++j)
-                if (k & (1 << j)) o |= 1ull << pass.spos[7 + j];
-            asm volatile("prefetch.global.L2 [%0];\n" ::"l"(nsrc + o));
-        }
-    };
-    const uint64_t tile_stride = gridDim.x;
-    uint64_t base = blockIdx.x < n_tiles ? tile_origin(blockIdx.x) : 0;
-    __syncthreads();  // the blob is staged
-    if (blockIdx.x < n_tiles) issue_tile(base);
-#if QC_K2T_PREFETCH
-    if (blockIdx.x + tile_stride < n_tiles) prefetch_tile(tile_origin(blockIdx.x + tile_stride));
-#endif
-    for (uint64_t tau = blockIdx.x; tau < n_tiles; tau += tile_stride) {
-        const bool has_next = tau + tile_stride < n_tiles;
-        const uint64_t next_base = has_next ? tile_origin(tau + tile_stride) : 0;
-#if QC_K2T_PREFETCH
-        if (tau + 2 * tile_stride < n_tiles) prefetch_tile(tile_origin(tau + 2 * tile_stride));
-#endif
         cp_async_wait_all();
-        __syncthreads();  // the tile has landed for every thread
+        __syncthreads();
 
         for (uint32_t rb = 0; rb < pass.n_rblocks; ++rb) {
             const uint4 b0 = blob[rb * kRBlockUnits];      // sbit[0..4], quad_mask
@@ -330,14 +291,6 @@ __global__ void __launch_bounds__(kTileThreads, 2)
                 if (p & 16) off ^= sb4;
                 a[p] = tile[off];
             }
-#if QC_K2T_EARLY
-            if (rb + 1 == pass.n_rblocks) {
-                // last visit of the tile: once the whole CTA has passed this barrier every sub-cube has been read
-                // (__syncthreads orders the shared-memory reads above before the writes of the copies below)
-                __syncthreads();
-                if (has_next) issue_tile(next_base);
-            }
-#endif
             const uint4* rp = blob + b1.x;
             const uint32_t rho8 = ((threadIdx.x >> 6) & 1u) * 8u;  // two-table records: units to skip for rho = 1
             // ---- simple quads of this cube (coordinate vectors of weight 4 and 3): straight-line code, no dispatch
@@ -419,16 +372,6 @@ __global__ void __launch_bounds__(kTileThreads, 2)
                 }
             }
         }
-#if !QC_K2T_EARLY
-        __syncthreads();  // tile fully consumed
-        if (has_next) issue_tile(next_base);
-#else
-        if (pass.n_rblocks == 0) {
-            __syncthreads();
-            if (has_next) issue_tile(next_base);
-        }
-#endif
-        base = next_base;
     }
     // CTA reduction (kTileThreads = 128 threads), fixed order => deterministic
     __shared__ double wpart[kTileThreads / 32];

@@ -28,44 +28,48 @@ namespace qc {
 constexpr int kHpThreads = 256;
 constexpr int kHpElems = kTileSize / kHpThreads;  // 16 elements per thread: tile-local bits 8..11
 
+// Per pass, everything the inner loops read besides the amplitudes is one BLOB of 16-byte units staged in shared memory
+// next to the tile (like K2T): [HpGroup x n_groups][HpSeg x n_segs][HpTerm x n_terms].  From global memory the three
+// dependent loads per x-mask (group -> segment -> terms) cost an L2 round trip each (the L1 is carved down to ~28 KB by the
+// tile) and the kernel ran latency-bound at a tenth of its shared-memory bound.
+constexpr uint32_t kHpBlobCapUnits = 2816;  // 44 KB: tile 64 KB + blob, two CTAs per SM
+
 struct HpPass {            // kernel parameter
     uint64_t s_mask;
     uint8_t spos[kTileBits];  // index-bit position of tile-local bit b (0..7 thread bits, 8..11 element bits)
-    uint32_t first_group, n_groups;
+    uint32_t blob_off;     // first unit of the pass's blob in the plan's unit array
+    uint32_t blob_units;
+    uint32_t n_groups, n_segs;
 };
 struct HpGroup {           // 16 bytes
     uint32_t x_loc;        // pairing mask in tile-local positions
-    uint32_t first_seg;
+    uint32_t first_seg;    // unit index inside the blob
     uint16_t n_seg_re, n_seg_im;  // segments of Re-type (even nY) terms first
     uint32_t pad;
 };
 struct HpSeg {             // 16 bytes
-    uint32_t first_term, n_terms;
+    uint32_t first_term;   // unit index inside the blob
+    uint32_t n_terms;
     uint32_t walsh;        // bit j = parity(j & z_j) of the segment's common z on the element bits
     uint32_t pad;
 };
-struct HpTerm {            // 32 bytes
-    uint64_t z_outer;      // z outside the tile (index-bit positions)
+struct HpTerm {            // 16 bytes
+    uint64_t z;            // bits 0..55: z outside the tile (index-bit positions, n <= 40); bits 56..63: z on the 8 thread bits
     double d;              // signed coefficient (conventions of hpsi_kernel)
-    uint32_t z_thr;        // z on the 8 thread bits (tile-local positions 0..7)
-    uint32_t pad[3];
 };
+static_assert(sizeof(HpGroup) == 16 && sizeof(HpSeg) == 16 && sizeof(HpTerm) == 16, "blob units");
 
 struct HpPlan {
     std::vector<uint64_t> key_x, key_z;
     std::vector<double> key_c;
     int n = 0;
     std::vector<HpPass> passes;
-    HpGroup* d_groups = nullptr;
-    HpSeg* d_segs = nullptr;
-    HpTerm* d_terms = nullptr;
+    uint4* d_units = nullptr;
     std::vector<uint64_t> left_x, left_z;
     std::vector<double> left_c;
     size_t n_groups = 0;
     ~HpPlan() {
-        if (d_groups) cudaFree(d_groups);
-        if (d_segs) cudaFree(d_segs);
-        if (d_terms) cudaFree(d_terms);
+        if (d_units) cudaFree(d_units);
     }
 };
 
@@ -82,10 +86,15 @@ __device__ __forceinline__ double hp_sign(double v, unsigned par) {
 
 __global__ void __launch_bounds__(kHpThreads, 2)
     hpsi_tiled_kernel(const double2* __restrict__ psi, double2* __restrict__ lam, int n, const HpPass pass,
-                      const HpGroup* __restrict__ groups, const HpSeg* __restrict__ segs, const HpTerm* __restrict__ terms,
-                      int accumulate) {
+                      const uint4* __restrict__ units, int accumulate) {
     extern __shared__ __align__(16) unsigned char hp_smem[];
     double2* tile = reinterpret_cast<double2*>(hp_smem);
+    const uint4* blob = reinterpret_cast<const uint4*>(hp_smem + (size_t)kTileSize * sizeof(double2));
+    {
+        uint4* dst = reinterpret_cast<uint4*>(hp_smem + (size_t)kTileSize * sizeof(double2));
+        const uint4* src = units + pass.blob_off;
+        for (uint32_t u = threadIdx.x; u < pass.blob_units; u += kHpThreads) dst[u] = __ldg(&src[u]);
+    }
     const uint32_t t = threadIdx.x;
     const uint64_t n_tiles = 1ull << (n - kTileBits);
     uint64_t off_thr = 0;
@@ -99,6 +108,7 @@ __global__ void __launch_bounds__(kHpThreads, 2)
             if (j & (1 << b)) o |= 1ull << pass.spos[8 + b];
         return o;
     };
+    const uint32_t t_hi = t << 24;  // thread bits aligned with bits 56..63 of a term's z word
     for (uint64_t tau = blockIdx.x; tau < n_tiles; tau += gridDim.x) {
         uint64_t base = tau;
         {
@@ -109,7 +119,7 @@ __global__ void __launch_bounds__(kHpThreads, 2)
                 m &= m - 1;
             }
         }
-        __syncthreads();  // previous tile fully consumed
+        __syncthreads();  // previous tile fully consumed (and, the first time, the blob staged)
         const double2* src = psi + base + off_thr;
 #pragma unroll
         for (int j = 0; j < kHpElems; ++j) hp_cp_async16(&tile[(uint32_t)j * kHpThreads + t], src + off_el(j));
@@ -125,50 +135,40 @@ __global__ void __launch_bounds__(kHpThreads, 2)
         asm volatile("cp.async.wait_all;\n" ::: "memory");
         __syncthreads();
 
-        const uint32_t base_lo = (uint32_t)base, base_hi = (uint32_t)(base >> 32);
+        // sign word of (tile origin, thread): parity of (word & term.z) = parity of (origin & z_outer) ^ (thread & z_thr)
+        const uint32_t sw_lo = (uint32_t)base, sw_hi = ((uint32_t)(base >> 32) & 0x00ffffffu) | t_hi;
+        uint4 gnext = blob[0];
         for (uint32_t g = 0; g < pass.n_groups; ++g) {
-            HpGroup gr;
-            {
-                const uint4 raw = __ldg(reinterpret_cast<const uint4*>(&groups[pass.first_group + g]));
-                gr.x_loc = raw.x, gr.first_seg = raw.y, gr.n_seg_re = (uint16_t)(raw.z & 0xffffu), gr.n_seg_im = (uint16_t)(raw.z >> 16);
-            }
-            const double2* partner = tile + (t ^ (gr.x_loc & 0xffu));
-            const uint32_t xj = gr.x_loc >> 8;
+            const uint4 graw = gnext;
+            if (g + 1 < pass.n_groups) gnext = blob[g + 1];  // the next header is in flight while this group runs
+            const uint32_t x_loc = graw.x;
+            const double2* partner = tile + (t ^ (x_loc & 0xffu));
+            const uint32_t xj = x_loc >> 8;
 #pragma unroll 1
             for (int type = 0; type < 2; ++type) {
-                const uint32_t s0 = gr.first_seg + (type ? gr.n_seg_re : 0u);
-                const uint32_t ns = type ? gr.n_seg_im : gr.n_seg_re;
+                const uint32_t s0 = graw.y + (type ? (graw.z & 0xffffu) : 0u);
+                const uint32_t ns = type ? (graw.z >> 16) : (graw.z & 0xffffu);
                 if (ns == 0) continue;
                 double w[kHpElems];
 #pragma unroll
                 for (int j = 0; j < kHpElems; ++j) w[j] = 0.0;
                 for (uint32_t s = 0; s < ns; ++s) {
-                    HpSeg sg;
-                    {
-                        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(&segs[s0 + s]));
-                        sg.first_term = raw.x, sg.n_terms = raw.y, sg.walsh = raw.z;
-                    }
+                    const uint4 sraw = blob[s0 + s];  // first_term, n_terms, walsh
+                    const uint4* tp = blob + sraw.x;
                     double b0 = 0.0, b1 = 0.0;
                     uint32_t k = 0;
-                    for (; k + 1 < sg.n_terms; k += 2) {
-                        const uint4 q0 = __ldg(reinterpret_cast<const uint4*>(&terms[sg.first_term + k]));
-                        const uint4 r0 = __ldg(reinterpret_cast<const uint4*>(&terms[sg.first_term + k]) + 1);
-                        const uint4 q1 = __ldg(reinterpret_cast<const uint4*>(&terms[sg.first_term + k + 1]));
-                        const uint4 r1 = __ldg(reinterpret_cast<const uint4*>(&terms[sg.first_term + k + 1]) + 1);
-                        const unsigned p0 = __popc((base_lo & q0.x) ^ (base_hi & q0.y) ^ (t & r0.x));
-                        const unsigned p1 = __popc((base_lo & q1.x) ^ (base_hi & q1.y) ^ (t & r1.x));
-                        b0 += hp_sign(__hiloint2double((int)q0.w, (int)q0.z), p0);
-                        b1 += hp_sign(__hiloint2double((int)q1.w, (int)q1.z), p1);
+                    for (; k + 1 < sraw.y; k += 2) {
+                        const uint4 q0 = tp[k], q1 = tp[k + 1];
+                        b0 += hp_sign(__hiloint2double((int)q0.w, (int)q0.z), __popc((sw_lo & q0.x) ^ (sw_hi & q0.y)));
+                        b1 += hp_sign(__hiloint2double((int)q1.w, (int)q1.z), __popc((sw_lo & q1.x) ^ (sw_hi & q1.y)));
                     }
-                    if (k < sg.n_terms) {
-                        const uint4 q0 = __ldg(reinterpret_cast<const uint4*>(&terms[sg.first_term + k]));
-                        const uint4 r0 = __ldg(reinterpret_cast<const uint4*>(&terms[sg.first_term + k]) + 1);
-                        const unsigned p0 = __popc((base_lo & q0.x) ^ (base_hi & q0.y) ^ (t & r0.x));
-                        b0 += hp_sign(__hiloint2double((int)q0.w, (int)q0.z), p0);
+                    if (k < sraw.y) {
+                        const uint4 q0 = tp[k];
+                        b0 += hp_sign(__hiloint2double((int)q0.w, (int)q0.z), __popc((sw_lo & q0.x) ^ (sw_hi & q0.y)));
                     }
                     const double bsum = b0 + b1;
 #pragma unroll
-                    for (int j = 0; j < kHpElems; ++j) w[j] += hp_sign(bsum, sg.walsh >> j);
+                    for (int j = 0; j < kHpElems; ++j) w[j] += hp_sign(bsum, sraw.z >> j);
                 }
                 if (type == 0) {
 #pragma unroll
@@ -237,9 +237,7 @@ static HpPlan* build_hp_plan(qc_state* h, size_t T, const uint64_t* hx, const ui
                 plan->left_c.push_back(hc[order[k]]);
             }
     }
-    std::vector<HpGroup> groups;
-    std::vector<HpSeg> segs;
-    std::vector<HpTerm> terms;
+    std::vector<Unit16> units;  // all blobs, back to back
     for (size_t p = 0; p < sets.size(); ++p) {
         if (members[p].empty()) continue;
         const uint64_t S = sets[p];
@@ -262,26 +260,65 @@ static HpPlan* build_hp_plan(qc_state* h, size_t T, const uint64_t* hx, const ui
             if (a0 != b0) return b0;
             return vary[a] < vary[b];
         });
-        HpPass pass;
-        memset(&pass, 0, sizeof(pass));
-        pass.s_mask = S;
+        HpPass base_pass;
+        memset(&base_pass, 0, sizeof(base_pass));
+        base_pass.s_mask = S;
         std::vector<int> el(idx.begin(), idx.begin() + 4), th(idx.begin() + 4, idx.end());
         std::sort(el.begin(), el.end());
         std::sort(th.begin(), th.end());
-        for (int b = 0; b < 8; ++b) pass.spos[b] = (uint8_t)sbits[th[b]];
-        for (int b = 0; b < 4; ++b) pass.spos[8 + b] = (uint8_t)sbits[el[b]];
+        for (int b = 0; b < 8; ++b) base_pass.spos[b] = (uint8_t)sbits[th[b]];
+        for (int b = 0; b < 4; ++b) base_pass.spos[8 + b] = (uint8_t)sbits[el[b]];
         auto to_local = [&](uint64_t m) {
             uint32_t out = 0;
             for (int b = 0; b < kTileBits; ++b)
-                if ((m >> pass.spos[b]) & 1ull) out |= 1u << b;
+                if ((m >> base_pass.spos[b]) & 1ull) out |= 1u << b;
             return out;
         };
-        pass.first_group = (uint32_t)groups.size();
+        // groups of the pass with their segments and terms; a blob that would exceed the cap starts another pass over S
+        struct GroupOut {
+            HpGroup hdr;
+            std::vector<HpSeg> segs;
+            std::vector<HpTerm> terms;  // seg.first_term relative to this vector until the blob is laid out
+        };
+        std::vector<GroupOut> cur;
+        uint32_t cur_units = 0;
+        auto flush = [&]() {
+            if (cur.empty()) return;
+            HpPass pass = base_pass;
+            pass.blob_off = (uint32_t)units.size();
+            pass.n_groups = (uint32_t)cur.size();
+            uint32_t n_segs = 0;
+            for (const GroupOut& go : cur) n_segs += (uint32_t)go.segs.size();
+            pass.n_segs = n_segs;
+            uint32_t seg_at = pass.n_groups, term_at = pass.n_groups + n_segs;
+            std::vector<Unit16> blob(term_at);
+            std::vector<Unit16> term_units;
+            uint32_t gi = 0;
+            for (GroupOut& go : cur) {
+                go.hdr.first_seg = seg_at;
+                for (HpSeg sg : go.segs) {
+                    sg.first_term += term_at + (uint32_t)term_units.size();
+                    memcpy(&blob[seg_at++], &sg, 16);
+                }
+                for (const HpTerm& tm : go.terms) {
+                    Unit16 u;
+                    memcpy(&u, &tm, 16);
+                    term_units.push_back(u);
+                }
+                memcpy(&blob[gi++], &go.hdr, 16);
+            }
+            blob.insert(blob.end(), term_units.begin(), term_units.end());
+            pass.blob_units = (uint32_t)blob.size();
+            units.insert(units.end(), blob.begin(), blob.end());
+            plan->passes.push_back(pass);
+            plan->n_groups += cur.size();
+            cur.clear();
+            cur_units = 0;
+        };
         for (size_t g : members[p]) {
-            HpGroup gr;
-            memset(&gr, 0, sizeof(gr));
-            gr.x_loc = to_local(xgs[g].x);
-            gr.first_seg = (uint32_t)segs.size();
+            GroupOut go;
+            memset(&go.hdr, 0, sizeof(go.hdr));
+            go.hdr.x_loc = to_local(xgs[g].x);
             for (int type = 0; type < 2; ++type) {
                 // segments keyed by the z pattern on the element bits
                 std::map<uint32_t, std::vector<HpTerm>> by_zj;
@@ -290,42 +327,47 @@ static HpPlan* build_hp_plan(qc_state* h, size_t T, const uint64_t* hx, const ui
                     const int ny = __builtin_popcountll(hx[tix] & hz[tix]);
                     if ((ny & 1) != type) continue;
                     HpTerm tm;
-                    memset(&tm, 0, sizeof(tm));
                     const uint32_t zl = to_local(hz[tix]);
-                    tm.z_outer = hz[tix] & ~S;
-                    tm.z_thr = zl & 0xffu;
+                    tm.z = (hz[tix] & ~S) | ((uint64_t)(zl & 0xffu) << 56);
                     tm.d = type ? -hc[tix] * ((((ny - 1) >> 1) & 1) ? -1.0 : 1.0) : hc[tix] * (((ny >> 1) & 1) ? -1.0 : 1.0);
                     by_zj[zl >> 8].push_back(tm);
                 }
                 for (auto& kv : by_zj) {
                     HpSeg sg;
                     memset(&sg, 0, sizeof(sg));
-                    sg.first_term = (uint32_t)terms.size();
+                    sg.first_term = (uint32_t)go.terms.size();
                     sg.n_terms = (uint32_t)kv.second.size();
                     for (uint32_t j = 0; j < 16; ++j)
                         if (__builtin_popcount(j & kv.first) & 1) sg.walsh |= 1u << j;
-                    terms.insert(terms.end(), kv.second.begin(), kv.second.end());
-                    segs.push_back(sg);
-                    (type ? gr.n_seg_im : gr.n_seg_re) += 1;
+                    go.terms.insert(go.terms.end(), kv.second.begin(), kv.second.end());
+                    go.segs.push_back(sg);
+                    (type ? go.hdr.n_seg_im : go.hdr.n_seg_re) += 1;
                 }
             }
-            groups.push_back(gr);
+            const uint32_t need = 1u + (uint32_t)go.segs.size() + (uint32_t)go.terms.size();
+            if (need > kHpBlobCapUnits) {  // a single x-mask with thousands of terms: left to the sweep kernel
+                for (size_t k = xgs[g].first; k < xgs[g].first + xgs[g].count; ++k) {
+                    plan->left_x.push_back(hx[order[k]]);
+                    plan->left_z.push_back(hz[order[k]]);
+                    plan->left_c.push_back(hc[order[k]]);
+                }
+                continue;
+            }
+            if (cur_units + need > kHpBlobCapUnits) flush();
+            cur_units += need;
+            cur.push_back(std::move(go));
         }
-        pass.n_groups = (uint32_t)groups.size() - pass.first_group;
-        plan->passes.push_back(pass);
+        flush();
     }
-    plan->n_groups = groups.size();
-    auto up = [&](void** dptr, const void* src, size_t bytes) {
-        if (cudaMalloc(dptr, std::max<size_t>(bytes, 16)) != cudaSuccess) return false;
-        return bytes == 0 || cudaMemcpy(*dptr, src, bytes, cudaMemcpyHostToDevice) == cudaSuccess;
-    };
-    if (!up((void**)&plan->d_groups, groups.data(), groups.size() * sizeof(HpGroup)) ||
-        !up((void**)&plan->d_segs, segs.data(), segs.size() * sizeof(HpSeg)) ||
-        !up((void**)&plan->d_terms, terms.data(), terms.size() * sizeof(HpTerm))) {
-        delete plan;
-        return nullptr;
+    {
+        const size_t bytes = std::max<size_t>(units.size(), 1) * sizeof(Unit16);
+        if (cudaMalloc((void**)&plan->d_units, bytes) != cudaSuccess ||
+            (!units.empty() && cudaMemcpy(plan->d_units, units.data(), units.size() * sizeof(Unit16), cudaMemcpyHostToDevice) != cudaSuccess)) {
+            delete plan;
+            return nullptr;
+        }
+        h->h2d_bytes += units.size() * sizeof(Unit16);
     }
-    h->h2d_bytes += groups.size() * sizeof(HpGroup) + segs.size() * sizeof(HpSeg) + terms.size() * sizeof(HpTerm);
     plan->key_x.assign(hx, hx + T);
     plan->key_z.assign(hz, hz + T);
     plan->key_c.assign(hc, hc + T);
@@ -349,7 +391,7 @@ int hpsi_tiled(qc_state* h, size_t T, const uint64_t* hx, const uint64_t* hz, co
         QC_REQUIRE(plan != nullptr, "qc_hpsi: could not build the tiled plan");
         h->hp_plan = plan;
     }
-    const size_t smem = (size_t)kTileSize * sizeof(double2);
+    const size_t smem = (size_t)kTileSize * sizeof(double2) + (size_t)kHpBlobCapUnits * 16;
     QC_CHECK(cudaFuncSetAttribute(hpsi_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     QC_CHECK(cudaFuncSetAttribute(hpsi_tiled_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     const uint64_t n_tiles = 1ull << (h->n - kTileBits);
@@ -361,8 +403,7 @@ int hpsi_tiled(qc_state* h, size_t T, const uint64_t* hx, const uint64_t* hz, co
             // algorithmic bytes: psi read + lambda read-modify-write per x-mask served (what the sweep version moves)
             LaunchScope ls(h, kGradient, 48.0 * (double)h->dim * (double)pass.n_groups);
             h->h2d_bytes += sizeof(HpPass);
-            hpsi_tiled_kernel<<<nb, kHpThreads, smem, h->stream>>>(h->psi, h->scratch_psi, h->n, pass, plan->d_groups, plan->d_segs,
-                                                                   plan->d_terms, acc ? 1 : 0);
+            hpsi_tiled_kernel<<<nb, kHpThreads, smem, h->stream>>>(h->psi, h->scratch_psi, h->n, pass, plan->d_units, acc ? 1 : 0);
         }
         QC_CHECK(cudaGetLastError());
         acc = true;

@@ -572,19 +572,6 @@ HostPlan* build_host_plan(int n, size_t T, const uint64_t* xs, const uint64_t* z
             pass.blob_off = (uint32_t)plan->units.size();
             pass.n_rblocks = (uint32_t)cur.size();
             pass.n_groups = cur_groups;
-            {
-                // The kernel issues the NEXT tile's loads right after the gather of a tile's LAST visit, so that they
-                // overlap that visit's records: the visit with the most record work goes last.
-                size_t richest = 0;
-                uint32_t best = 0;
-                for (size_t i = 0; i < cur.size(); ++i) {
-                    uint32_t c = (uint32_t)cur[i].recs.size();
-                    for (int j = 0; j < kQuadSlots; ++j) c += (uint32_t)cur[i].quads[j].size();
-                    for (int j = 0; j < kHopSlots; ++j) c += (uint32_t)cur[i].hops[j].size();
-                    if (c >= best) best = c, richest = i;
-                }
-                if (richest + 1 != cur.size()) std::swap(cur[richest], cur.back());
-            }
             uint32_t rec_off = (uint32_t)cur.size() * kRBlockUnits;
             for (RB& rb : cur) {
                 pass.n_generic += rb.hdr.n_recs + (uint32_t)popc32(rb.hdr.hop_mask);

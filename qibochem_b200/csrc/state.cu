@@ -180,6 +180,7 @@ int qc_destroy(qc_state* h) {
     h->prof.release();
     for (qc::TiledPlan* p : h->k2plans) qc::free_tiled_plan(p);
     if (h->hp_plan) qc::free_hp_plan(h->hp_plan);
+    if (h->sweep_plan) qc::free_sweep_plan(h->sweep_plan);
     if (h->owns_stream) cudaStreamDestroy(h->stream);
     delete h;
     return 0;

@@ -152,7 +152,10 @@ class SymbolicHamiltonian:
             st = get_runtime().state(self.nqubits)
             st.from_numpy(psi)
         x, z, c = self.index_masks()
-        norm = st.norm2() if self._constant else 1.0
+        # <psi|psi> multiplies the identity term; a circuit run from a basis state is unitary, so the extra reduction
+        # (a launch and a device->host read per energy) is only paid for states the caller supplied
+        prepared_here = isinstance(circuit_or_state, Circuit)
+        norm = st.norm2() if (self._constant and not prepared_here) else 1.0
         return self._constant * norm + st.expectation(x, z, c)
 
     def expectation_from_samples(self, freq: dict, qubit_map=None) -> float:
