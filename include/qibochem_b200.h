@@ -72,7 +72,11 @@ int qc_expectation(qc_state* h, size_t T, const uint64_t* xmask, const uint64_t*
  * HBM read (needs >= 12 local qubits; falls back to sweeps for x-masks that do not fit a tile).
  * "k1_mode" = 0 auto (default: consecutive fused runs with linearly independent x-masks -- up to 5 distinct ones --
  * are applied from registers in one in-place HBM pass), 1 one HBM pass per fused run, 2 shared-memory tiles
- * (consecutive runs whose x-masks fit a 12-bit tile), 3 register phases even for a lone run. */
+ * (consecutive runs whose x-masks fit a 12-bit tile), 3 register phases even for a lone run.
+ * "k2_real" = 1: the tiled expectation checks (one read of the shard) whether every imaginary part is exactly zero --
+ * true for a Hartree-Fock determinant evolved by UCC rotations -- and then runs real-amplitude kernels (one
+ * multiplication per pair product, odd-nY terms vanish, three CTAs per SM); default 0: always the complex128 kernels.
+ * ("k2_real_taken", any value) returns 0 if the last tiled expectation took the real path, 3 if not. */
 int qc_set_option(qc_state* h, const char* key, int64_t value);
 /* Host-only (no GPU needed): plans the tiled expectation of a term list and reports its shape.  stats_out: 16 x
  * uint64 {x-masks, tiled x-masks, HBM passes, register sub-cubes, DOT records, LIN entries, leftover terms (sweep

@@ -96,6 +96,8 @@ struct qc_state {
     qc::SweepPlan* sweep_plan = nullptr;  // grouped device program of the last term list the sweep kernel ran
     qc::HpPlan* hp_plan = nullptr;        // cached plan of the tiled H|psi> (adjoint gradient), last term list only
     int k1_mode = 0;                  // 0 auto, 1 one HBM pass per fused run, 2 shared-memory tiles whenever a run fits
+    int k2_real = 0;                  // 1: tiled expectation through the real-amplitude kernels when the shard is exactly real
+    int last_k2_real = 0;             // whether the last tiled expectation took them
     int k2_mode = 0;                  // 0 auto, 1 force sweeps (one HBM pass per x-mask), 2 force tiles
     int ensure_partials(size_t doubles);
     int ensure_out(size_t doubles);

@@ -22,6 +22,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <type_traits>
 
 #include "common.cuh"
 #include "k2_plan.h"
@@ -63,6 +64,24 @@ __device__ __forceinline__ double apply_sign(double v, unsigned par) {
     return __longlong_as_double(__double_as_longlong(v) ^ ((long long)(par & 1u) << 63));
 }
 
+// Amplitude arithmetic for the two register representations of a sub-cube: complex128 (double2) and REAL (double: the
+// "k2_real" fast path, taken only when every imaginary part of the shard is exactly zero -- a HF determinant evolved by
+// UCC rotations, whose strings all carry an odd number of Y, stays real).  For a real state Re(conj(a) b) is ONE
+// multiplication, Im(conj(a) b) vanishes (odd-nY Hamiltonian terms contribute nothing), a sub-cube is 64 registers
+// instead of 128 and a tile 32 KB instead of 64 KB.
+__device__ __forceinline__ double re0(const double2& a, const double2& b) { return a.x * b.x; }
+__device__ __forceinline__ double re1(const double2& a, const double2& b, double pr) { return fma(a.y, b.y, pr); }
+__device__ __forceinline__ double im0(const double2& a, const double2& b) { return a.x * b.y; }
+__device__ __forceinline__ double im1(const double2& a, const double2& b, double pr) { return fma(-a.y, b.x, pr); }
+__device__ __forceinline__ double abs2(const double2& a) { return a.x * a.x + a.y * a.y; }
+__device__ __forceinline__ void keep(double2& a) { asm volatile("" : "+d"(a.x), "+d"(a.y)); }
+__device__ __forceinline__ double re0(double a, double b) { return a * b; }
+__device__ __forceinline__ double re1(double, double, double pr) { return pr; }
+__device__ __forceinline__ double im0(double, double) { return 0.0; }
+__device__ __forceinline__ double im1(double, double, double pr) { return pr; }
+__device__ __forceinline__ double abs2(double a) { return a * a; }
+__device__ __forceinline__ void keep(double& a) { asm volatile("" : "+d"(a)); }
+
 // w = sum_k tab[k] * prod_k over the 16 canonical pairs {p, p^XR} of the sub-cube (p ascending, highest bit of XR
 // clear); prod = Re or Im of conj(a_p) a_{p^XR}.  Everything is static register indexing; 4 independent FMA chains.
 // k-th canonical pair index (p has the highest bit HB of XR clear; ascending)
@@ -71,8 +90,8 @@ __device__ __forceinline__ constexpr int pair_index(int k) {
     return ((k / HB) * 2 * HB) | (k % HB);
 }
 
-template <int XR, bool IM>
-__device__ __forceinline__ double dot_pairs(const double2 (&a)[32], const double2* __restrict__ tab) {
+template <int XR, bool IM, typename A>
+__device__ __forceinline__ double dot_pairs(const A (&a)[32], const double2* __restrict__ tab) {
     constexpr int HB = XR >= 16 ? 16 : XR >= 8 ? 8 : XR >= 4 ? 4 : XR >= 2 ? 2 : 1;
     double w[4] = {0.0, 0.0, 0.0, 0.0};
     // two batches of 8 pairs; inside a batch the three dependent steps of a pair are 8 instructions apart
@@ -85,12 +104,12 @@ __device__ __forceinline__ double dot_pairs(const double2 (&a)[32], const double
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int p = pair_index<HB>(8 * b + j);
-            pr[j] = IM ? a[p].x * a[p ^ XR].y : a[p].x * a[p ^ XR].x;
+            pr[j] = IM ? im0(a[p], a[p ^ XR]) : re0(a[p], a[p ^ XR]);
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int p = pair_index<HB>(8 * b + j);
-            pr[j] = IM ? fma(-a[p].y, a[p ^ XR].x, pr[j]) : fma(a[p].y, a[p ^ XR].y, pr[j]);
+            pr[j] = IM ? im1(a[p], a[p ^ XR], pr[j]) : re1(a[p], a[p ^ XR], pr[j]);
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) w[j & 3] = fma(pr[j], (j & 1) ? t[j >> 1].y : t[j >> 1].x, w[j & 3]);
@@ -100,8 +119,8 @@ __device__ __forceinline__ double dot_pairs(const double2 (&a)[32], const double
 
 // The same as dot_pairs<XR, false> but leaves the four partial sums to the caller, which folds them one record later
 // (the dependent tail of a record then overlaps the products of the next one).
-template <int XR>
-__device__ __forceinline__ void dot_pairs4(const double2 (&a)[32], const double2* __restrict__ tab, double (&w)[4]) {
+template <int XR, typename A>
+__device__ __forceinline__ void dot_pairs4(const A (&a)[32], const double2* __restrict__ tab, double (&w)[4]) {
     constexpr int HB = XR >= 16 ? 16 : XR >= 8 ? 8 : XR >= 4 ? 4 : XR >= 2 ? 2 : 1;
     w[0] = w[1] = w[2] = w[3] = 0.0;
 #pragma unroll
@@ -113,28 +132,27 @@ __device__ __forceinline__ void dot_pairs4(const double2 (&a)[32], const double2
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int p = pair_index<HB>(8 * b + j);
-            pr[j] = a[p].x * a[p ^ XR].x;
+            pr[j] = re0(a[p], a[p ^ XR]);
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int p = pair_index<HB>(8 * b + j);
-            pr[j] = fma(a[p].y, a[p ^ XR].y, pr[j]);
+            pr[j] = re1(a[p], a[p ^ XR], pr[j]);
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) w[j & 3] = fma(pr[j], (j & 1) ? t[j >> 1].y : t[j >> 1].x, w[j & 3]);
     }
 }
 
-template <int HALF>
-__device__ __forceinline__ double dot_diag(const double2 (&a)[32], const double2* __restrict__ tab) {
+template <int HALF, typename A>
+__device__ __forceinline__ double dot_diag(const A (&a)[32], const double2* __restrict__ tab) {
     double2 t[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) t[j] = tab[j];
     double w[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
-        const double2 v = a[k + 16 * HALF];
-        const double pr = v.x * v.x + v.y * v.y;
+        const double pr = abs2(a[k + 16 * HALF]);
         const double tk = (k & 1) ? t[k >> 1].y : t[k >> 1].x;
         w[k & 3] = fma(pr, tk, w[k & 3]);
     }
@@ -142,8 +160,8 @@ __device__ __forceinline__ double dot_diag(const double2 (&a)[32], const double2
 }
 
 // HOP record (k2_plan.h): three tables weight the same 16 products; two accumulators per table => six independent chains
-template <int XR>
-__device__ __forceinline__ void dot3(const double2 (&a)[32], const double2* __restrict__ tab_acc,
+template <int XR, typename A>
+__device__ __forceinline__ void dot3(const A (&a)[32], const double2* __restrict__ tab_acc,
                                      const double2* __restrict__ tab_pat, double& w_acc, double& A0, double& A1) {
     constexpr int HB = XR >= 16 ? 16 : XR >= 8 ? 8 : XR >= 4 ? 4 : XR >= 2 ? 2 : 1;
     double w[3][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
@@ -153,12 +171,12 @@ __device__ __forceinline__ void dot3(const double2 (&a)[32], const double2* __re
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int p = pair_index<HB>(8 * b + j);
-            pr[j] = a[p].x * a[p ^ XR].x;
+            pr[j] = re0(a[p], a[p ^ XR]);
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int p = pair_index<HB>(8 * b + j);
-            pr[j] = fma(a[p].y, a[p ^ XR].y, pr[j]);
+            pr[j] = re1(a[p], a[p ^ XR], pr[j]);
         }
 #pragma unroll
         for (int t = 0; t < 3; ++t) {
@@ -176,7 +194,8 @@ __device__ __forceinline__ void dot3(const double2 (&a)[32], const double2* __re
 
 // sel = xr | im << 5 for DOT records; 0 / 32 = lower / upper half of a diagonal record.  All 64 values are cases, so
 // the switch compiles to ONE jump table.
-__device__ __forceinline__ double dot_dispatch(uint32_t sel, const double2 (&a)[32], const double2* __restrict__ tab) {
+template <typename A>
+__device__ __forceinline__ double dot_dispatch(uint32_t sel, const A (&a)[32], const double2* __restrict__ tab) {
 #define QC_CASE(X)                              \
     case X: return dot_pairs<X, false>(a, tab); \
     case 32 + X: return dot_pairs<X, true>(a, tab);
@@ -199,8 +218,8 @@ __device__ __forceinline__ unsigned sign_parity(uint64_t base, uint32_t org, con
 }
 
 // One HOP record: ACC table + two pattern sums combined by 32-byte entries; returns the next record
-template <int XR>
-__device__ __forceinline__ const uint4* hop_record(const double2 (&a)[32], const uint4* __restrict__ rp, uint64_t base,
+template <int XR, typename A>
+__device__ __forceinline__ const uint4* hop_record(const A (&a)[32], const uint4* __restrict__ rp, uint64_t base,
                                                    uint32_t org, uint32_t rho, double& acc0, double& acc1) {
     const uint4 hd = *rp;
     double w, A0, A1;
@@ -229,15 +248,23 @@ __device__ __forceinline__ const uint4* hop_record(const double2 (&a)[32], const
 // 2 CTAs per SM.  Everything the inner loops read besides the amplitudes comes from shared memory (broadcast LDS)
 // or the constant bank (TPass), so no global-load latency sits on the critical path.
 // GENERIC = false: the pass holds simple quads only (the common case) and the record loop is compiled out.
-template <bool GENERIC>
-__global__ void __launch_bounds__(kTileThreads, 2)
+// REAL = true: the "k2_real" fast path (see the amplitude helpers above): the tile holds real parts only (32 KB), a
+// sub-cube is 64 registers, so THREE CTAs fit an SM (170 registers per thread, 32 KB + the pass's own blob each).
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+    const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gmem));
+}
+
+template <bool GENERIC, bool REAL>
+__global__ void __launch_bounds__(kTileThreads, REAL ? 3 : 2)
     expectation_tiled_kernel(const double2* __restrict__ psi, int n, const TPass pass, const uint4* __restrict__ units,
                              double* __restrict__ partials) {
+    using A = typename std::conditional<REAL, double, double2>::type;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double2* tile = reinterpret_cast<double2*>(smem_raw);
-    const uint4* blob = reinterpret_cast<const uint4*>(smem_raw + (size_t)kTileSize * sizeof(double2));
+    A* tile = reinterpret_cast<A*>(smem_raw);
+    const uint4* blob = reinterpret_cast<const uint4*>(smem_raw + (size_t)kTileSize * sizeof(A));
     {
-        uint4* dst = reinterpret_cast<uint4*>(smem_raw + (size_t)kTileSize * sizeof(double2));
+        uint4* dst = reinterpret_cast<uint4*>(smem_raw + (size_t)kTileSize * sizeof(A));
         const uint4* src = units + pass.blob_off;
         for (uint32_t u = threadIdx.x; u < pass.blob_units; u += kTileThreads) dst[u] = __ldg(&src[u]);
     }
@@ -267,7 +294,10 @@ __global__ void __launch_bounds__(kTileThreads, 2)
 #pragma unroll
             for (int j = 0; j < 5; ++j)
                 if (k & (1 << j)) o |= 1ull << pass.spos[7 + j];
-            cp_async16(&tile[k2_swizzle((uint32_t)k * kTileThreads + threadIdx.x)], src + o);
+            if (REAL)
+                cp_async8(&tile[k2_swizzle((uint32_t)k * kTileThreads + threadIdx.x)], &src[o].x);
+            else
+                cp_async16(&tile[k2_swizzle((uint32_t)k * kTileThreads + threadIdx.x)], src + o);
         }
         cp_async_wait_all();
         __syncthreads();
@@ -280,7 +310,7 @@ __global__ void __launch_bounds__(kTileThreads, 2)
             const uint32_t packed = otab[threadIdx.x & 15u] ^ otab[16u + (threadIdx.x >> 4)];
             const uint32_t org = packed >> 16, org_sw = packed & 0xffffu;
             const uint32_t sb0 = b0.x & 0xffffu, sb1 = b0.x >> 16, sb2 = b0.y & 0xffffu, sb3 = b0.y >> 16, sb4 = b0.z & 0xffffu;
-            double2 a[32];
+            A a[32];
 #pragma unroll
             for (int p = 0; p < 32; ++p) {
                 uint32_t off = org_sw;
@@ -353,7 +383,7 @@ __global__ void __launch_bounds__(kTileThreads, 2)
                 // The products below depend only on a[], which is invariant in this loop: without this barrier the
                 // compiler hoists the products of EVERY switch case out of the loop (LICM) and spills.
 #pragma unroll
-                for (int p = 0; p < 32; ++p) asm volatile("" : "+d"(a[p].x), "+d"(a[p].y));
+                for (int p = 0; p < 32; ++p) keep(a[p]);
                 const uint32_t sel = kind == kRecDot ? (meta & 63u) : (kind == kRecDiagHi ? 32u : 0u);
                 const uint32_t two = (meta >> 12) & 1u;
                 const double w = dot_dispatch(sel, a, reinterpret_cast<const double2*>(rp + 1 + two * rho8));
@@ -385,6 +415,32 @@ __global__ void __launch_bounds__(kTileThreads, 2)
         for (int k = 0; k < kTileThreads / 32; ++k) t += wpart[k];
         partials[blockIdx.x] = t;
     }
+}
+
+// sum_i |Im psi_i| over the shard (exactly 0 <=> the state is real): partials[b] per CTA
+__global__ void __launch_bounds__(kThreads) imag_abs_sum_kernel(const double2* __restrict__ psi, uint64_t dim,
+                                                                double* __restrict__ partials) {
+    double acc = 0.0;
+    for (uint64_t i = (uint64_t)blockIdx.x * kThreads + threadIdx.x; i < dim; i += (uint64_t)gridDim.x * kThreads)
+        acc += fabs(psi[i].y);
+    const double t = block_sum(acc);
+    if (threadIdx.x == 0) partials[blockIdx.x] = t;
+}
+
+static int imag_abs_sum(qc_state* h, double* out) {
+    const int nb = grid_for(h->dim, 4, h->sm_count);
+    if (h->ensure_partials((size_t)nb) || h->ensure_out(1)) return 1;
+    {
+        LaunchScope ls(h, kReduce, 16.0 * (double)h->dim);
+        imag_abs_sum_kernel<<<nb, kThreads, 0, h->stream>>>(h->psi, h->dim, h->d_partials);
+    }
+    QC_CHECK(cudaGetLastError());
+    if (fold_partials(h, h->d_partials, 1, nb, nb, h->d_out)) return 1;
+    QC_CHECK(cudaMemcpyAsync(h->h_out, h->d_out, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    h->d2h_bytes += sizeof(double);
+    QC_CHECK(cudaStreamSynchronize(h->stream));
+    *out = h->h_out[0];
+    return 0;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -451,10 +507,24 @@ int run_tiled_expectation(qc_state* h, size_t T, const uint64_t* xs, const uint6
     h->k2plans.push_back(found);  // most recently used last
     const TiledPlan* plan = found;
     const HostPlan* hp = plan->host;
-    const size_t smem = (size_t)kTileSize * sizeof(double2) + (size_t)kBlobCapUnits * 16;
-    const int ctas = 2;
-    for (auto kernel : {expectation_tiled_kernel<true>, expectation_tiled_kernel<false>}) {
-        QC_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // "k2_real": the real-amplitude kernels, only when every imaginary part of the shard is EXACTLY zero (checked here,
+    // one read of the shard per call); anything else runs the complex kernels
+    bool real = false;
+    if (h->k2_real) {
+        double im_sum = 1.0;
+        if (imag_abs_sum(h, &im_sum)) return 1;
+        real = im_sum == 0.0;
+    }
+    h->last_k2_real = real ? 1 : 0;
+    const size_t smem_complex = (size_t)kTileSize * sizeof(double2) + (size_t)kBlobCapUnits * 16;
+    const size_t smem_real_max = (size_t)kTileSize * sizeof(double) + (size_t)kBlobCapUnits * 16;
+    const int ctas = real ? 3 : 2;
+    for (auto kernel : {expectation_tiled_kernel<true, false>, expectation_tiled_kernel<false, false>}) {
+        QC_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_complex));
+        QC_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    }
+    for (auto kernel : {expectation_tiled_kernel<true, true>, expectation_tiled_kernel<false, true>}) {
+        QC_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_real_max));
         QC_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     }
     const uint64_t n_tiles = 1ull << (h->n - kTileBits);
@@ -468,8 +538,21 @@ int run_tiled_expectation(qc_state* h, size_t T, const uint64_t* xs, const uint6
         {
             LaunchScope ls(h, kK2Tiled, 16.0 * (double)h->dim * (double)pass.n_groups);
             h->h2d_bytes += sizeof(TPass);
-            auto kernel = pass.n_generic ? expectation_tiled_kernel<true> : expectation_tiled_kernel<false>;
-            kernel<<<nb, kTileThreads, smem, h->stream>>>(h->psi, h->n, pass, plan->d_units, h->d_partials + p * nb);
+            if (real) {
+                // shared memory = the tile + THIS pass's blob: passes whose blob stays below ~43 KB run three CTAs per SM
+                const size_t smem = (size_t)kTileSize * sizeof(double) + (((size_t)pass.blob_units * 16 + 1023) & ~(size_t)1023);
+                auto kernel = pass.n_generic ? expectation_tiled_kernel<true, true> : expectation_tiled_kernel<false, true>;
+                // a persistent grid must not exceed what is resident at once (a pass with a full 44 KB blob fits two
+                // CTAs per SM, the others three); unused partial slots of the pass are zeroed
+                int occ = 2;
+                QC_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kTileThreads, smem));
+                const int nbp = (int)std::min<uint64_t>(n_tiles, (uint64_t)h->sm_count * (uint64_t)std::max(1, std::min(occ, ctas)));
+                if (nbp < nb) QC_CHECK(cudaMemsetAsync(h->d_partials + p * nb + nbp, 0, (size_t)(nb - nbp) * sizeof(double), h->stream));
+                kernel<<<nbp, kTileThreads, smem, h->stream>>>(h->psi, h->n, pass, plan->d_units, h->d_partials + p * nb);
+            } else {
+                auto kernel = pass.n_generic ? expectation_tiled_kernel<true, false> : expectation_tiled_kernel<false, false>;
+                kernel<<<nb, kTileThreads, smem_complex, h->stream>>>(h->psi, h->n, pass, plan->d_units, h->d_partials + p * nb);
+            }
         }
         QC_CHECK(cudaGetLastError());
     }

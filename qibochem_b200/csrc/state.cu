@@ -243,6 +243,14 @@ int qc_set_option(qc_state* h, const char* key, int64_t value) {
         h->k1_mode = (int)value;
         return 0;
     }
+    if (strcmp(key, "k2_real") == 0) {
+        QC_REQUIRE(value == 0 || value == 1, "qc_set_option: k2_real must be 0 or 1");
+        h->k2_real = (int)value;
+        return 0;
+    }
+    if (strcmp(key, "k2_real_taken") == 0) {  // query: did the last tiled expectation run the real-amplitude kernels?
+        return h->last_k2_real ? 0 : 3;
+    }
     qc::set_error(std::string("qc_set_option: unknown key ") + key);
     return 2;
 }

@@ -279,6 +279,10 @@ class DeviceState:
         """e.g. ``set_option("k2_mode", 1)``: 0 auto, 1 sweeps (one HBM pass per x-mask), 2 tiles."""
         _native.check(self._lib.qc_set_option(self._h, key.encode(), int(value)), "qc_set_option")
 
+    def took_real_path(self) -> bool:
+        """Whether the last tiled expectation ran the real-amplitude kernels (option ``k2_real``)."""
+        return self._lib.qc_set_option(self._h, b"k2_real_taken", 0) == 0
+
     def transfer_bytes(self, reset: bool = False) -> tuple[int, int]:
         """(host->device, device->host) bytes moved by the compute entry points since the last reset."""
         a, b = C.c_uint64(0), C.c_uint64(0)

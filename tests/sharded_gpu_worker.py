@@ -79,7 +79,7 @@ def public_api(rank, world, local_rank):
     assert abs(e - e_ref) < 1e-11, (e, e_ref)
     assert np.abs(c().state() - psi).max() < 1e-12
     # VQE-style loop: new parameters, same compiled program
-    params = np.array([p[0] for p in c.get_parameters()], dtype=float) * 0.7
+    params = np.array([complex(p[0]).real for p in c.get_parameters()], dtype=float) * 0.7  # ucc parameters are complex-typed
     c.set_parameters(params)
     prog = c.program()
     psi2 = np.zeros(2**n, dtype=complex)

@@ -792,3 +792,36 @@ def test_adjoint_gradient_through_tiles(DeviceState, n):
             up[k] += np.pi / 2
             dn[k] -= np.pi / 2
             assert abs(grads[2][k] - 0.5 * (energy(up, 1) - energy(dn, 1))) < 1e-10
+
+
+@pytest.mark.parametrize("n", [13, 16, 18])
+def test_real_amplitude_fast_path(DeviceState, n):
+    """Option k2_real: a HF determinant evolved by UCC rotations (every string has an odd number of Y) is exactly real,
+    the tiled expectation then runs the real-amplitude kernels: same energy as the complex kernels and the oracle,
+    odd-nY Hamiltonian terms included (they contribute exactly 0 on a real state).  A complex state must NOT take
+    the path."""
+    from oracle import oracle_c as OC
+    from qibochem_b200 import synthetic
+
+    ne = 6
+    rx, rz, ra, _ = synthetic.uccsd_rotation_stream(n, ne, max_excitations=30)
+    hx, hz, hc = _hpsi_inputs(n, 60 + n)  # molecular-structured + random strings (odd nY among them) + a wide x-mask
+    with DeviceState(n) as st:
+        st.set_basis_state(synthetic.hf_index(n, ne))
+        st.apply_pauli_rotations(rx, rz, ra)
+        psi = st.to_numpy()
+        assert np.abs(psi.imag).max() == 0.0  # exactly real, not merely small
+        st.set_option("k2_mode", 2)
+        e_complex = st.expectation(hx, hz, hc)
+        assert not st.took_real_path()
+        st.set_option("k2_real", 1)
+        e_real = st.expectation(hx, hz, hc)
+        assert st.took_real_path()
+        ref = OC.expectation_masks(psi, n, hx, hz, hc)
+        assert abs(e_complex - ref) < E_TOL and abs(e_real - ref) < E_TOL
+        # a state with imaginary parts: the check fails and the complex kernels run
+        st.apply_pauli_rotations([0], [1], [0.3])  # exp(-i 0.15 Z_{n-1}): diagonal phase
+        e_c = st.expectation(hx, hz, hc)
+        assert not st.took_real_path()
+        st.set_option("k2_real", 0)
+        assert abs(st.expectation(hx, hz, hc) - e_c) < 1e-13
