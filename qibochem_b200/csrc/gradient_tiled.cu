@@ -149,11 +149,8 @@ __global__ void __launch_bounds__(kHpThreads, 2)
                 const uint32_t s0 = graw.y + (type ? (graw.z & 0xffffu) : 0u);
                 const uint32_t ns = type ? (graw.z >> 16) : (graw.z & 0xffffu);
                 if (ns == 0) continue;
-                double w[kHpElems];
-#pragma unroll
-                for (int j = 0; j < kHpElems; ++j) w[j] = 0.0;
-                for (uint32_t s = 0; s < ns; ++s) {
-                    const uint4 sraw = blob[s0 + s];  // first_term, n_terms, walsh
+                // signed sum of a segment's coefficients for this (tile origin, thread)
+                auto segment_sum = [&](const uint4& sraw) {
                     const uint4* tp = blob + sraw.x;
                     double b0 = 0.0, b1 = 0.0;
                     uint32_t k = 0;
@@ -166,7 +163,48 @@ __global__ void __launch_bounds__(kHpThreads, 2)
                         const uint4 q0 = tp[k];
                         b0 += hp_sign(__hiloint2double((int)q0.w, (int)q0.z), __popc((sw_lo & q0.x) ^ (sw_hi & q0.y)));
                     }
-                    const double bsum = b0 + b1;
+                    return b0 + b1;
+                };
+                if (ns == 1) {
+                    // ONE segment (the common case: the element bits are chosen where the z-masks are emptiest): the 16
+                    // weights are +-bsum, no weight array; with an empty Walsh word not even a sign
+                    const uint4 sraw = blob[s0];
+                    const double bsum = segment_sum(sraw);
+                    const uint32_t walsh = sraw.z;
+                    if (walsh == 0u) {
+#pragma unroll
+                        for (int j = 0; j < kHpElems; ++j) {
+                            const double2 v = partner[(uint32_t)(j ^ xj) * kHpThreads];
+                            if (type == 0) {
+                                acc[j].x = fma(bsum, v.x, acc[j].x);
+                                acc[j].y = fma(bsum, v.y, acc[j].y);
+                            } else {
+                                acc[j].x = fma(-bsum, v.y, acc[j].x);
+                                acc[j].y = fma(bsum, v.x, acc[j].y);
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < kHpElems; ++j) {
+                            const double2 v = partner[(uint32_t)(j ^ xj) * kHpThreads];
+                            const double wj = hp_sign(bsum, walsh >> j);
+                            if (type == 0) {
+                                acc[j].x = fma(wj, v.x, acc[j].x);
+                                acc[j].y = fma(wj, v.y, acc[j].y);
+                            } else {
+                                acc[j].x = fma(-wj, v.y, acc[j].x);
+                                acc[j].y = fma(wj, v.x, acc[j].y);
+                            }
+                        }
+                    }
+                    continue;
+                }
+                double w[kHpElems];
+#pragma unroll
+                for (int j = 0; j < kHpElems; ++j) w[j] = 0.0;
+                for (uint32_t s = 0; s < ns; ++s) {
+                    const uint4 sraw = blob[s0 + s];  // first_term, n_terms, walsh
+                    const double bsum = segment_sum(sraw);
 #pragma unroll
                     for (int j = 0; j < kHpElems; ++j) w[j] += hp_sign(bsum, sraw.z >> j);
                 }
@@ -241,18 +279,17 @@ static HpPlan* build_hp_plan(qc_state* h, size_t T, const uint64_t* hx, const ui
     for (size_t p = 0; p < sets.size(); ++p) {
         if (members[p].empty()) continue;
         const uint64_t S = sets[p];
-        // element bits: the 4 tile bits (never index bit 0) on which the z-masks of the pass's groups vary least
+        // element bits: the 4 tile bits (never index bit 0) that the z-masks of the pass's terms touch least
         std::vector<int> sbits;
         for (int b = 0; b < 64; ++b)
             if ((S >> b) & 1ull) sbits.push_back(b);
+        // score of a tile bit: how many terms of the pass carry z there (a bit no z touches keeps every group at one
+        // segment with an empty Walsh word: the kernel's cheapest path)
         std::vector<uint64_t> vary(sbits.size(), 0);
-        for (size_t g : members[p]) {
-            uint64_t d = 0;
-            const uint64_t z0 = hz[order[xgs[g].first]];
-            for (size_t k = xgs[g].first; k < xgs[g].first + xgs[g].count; ++k) d |= hz[order[k]] ^ z0;
-            for (size_t i = 0; i < sbits.size(); ++i)
-                if ((d >> sbits[i]) & 1ull) vary[i] += 1;
-        }
+        for (size_t g : members[p])
+            for (size_t k = xgs[g].first; k < xgs[g].first + xgs[g].count; ++k)
+                for (size_t i = 0; i < sbits.size(); ++i)
+                    if ((hz[order[k]] >> sbits[i]) & 1ull) vary[i] += 1;
         std::vector<size_t> idx(sbits.size());
         std::iota(idx.begin(), idx.end(), (size_t)0);
         std::stable_sort(idx.begin(), idx.end(), [&](size_t a, size_t b) {
