@@ -61,6 +61,12 @@ int qc_set_basis_state(qc_state* h, uint64_t index, int has_one);
 int qc_apply_pauli_rotations(qc_state* h, size_t R, const uint64_t* xmask, const uint64_t* zmask,
                              const double* angle, int* n_passes_out);
 
+/* K0 + K1 in one call (what Circuit.__call__ does for hf_circuit + ucc_circuit, src/qibochem/ansatz/ansatz.py:253-350):
+ * identical to qc_set_basis_state followed by qc_apply_pauli_rotations; on a small register (<= 13 local qubits) the
+ * basis state and the WHOLE program run in one launch with the state in shared memory. */
+int qc_prepare_state(qc_state* h, uint64_t basis_index, int has_one, size_t R, const uint64_t* xmask,
+                     const uint64_t* zmask, const double* angle, int* n_passes_out);
+
 /* ---- K2: exact expectation  (replaces SymbolicHamiltonian.expectation(circuit), called e.g. at
  *      tests/test_ansatz.py:131, examples/ucc_example1.py:45) ------------------------------------------------ */
 /* energy_out <- sum_k coeff[k] * Re<psi|P_k|psi> over this shard (no constant term; the host adds it and

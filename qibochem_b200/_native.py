@@ -29,6 +29,7 @@ SIGNATURES = {
     "qc_synchronize": (C.c_int, [_vp]),
     "qc_set_basis_state": (C.c_int, [_vp, C.c_uint64, C.c_int]),
     "qc_apply_pauli_rotations": (C.c_int, [_vp, C.c_size_t, _u64p, _u64p, _f64p, C.POINTER(C.c_int)]),
+    "qc_prepare_state": (C.c_int, [_vp, C.c_uint64, C.c_int, C.c_size_t, _u64p, _u64p, _f64p, C.POINTER(C.c_int)]),
     "qc_expectation": (C.c_int, [_vp, C.c_size_t, _u64p, _u64p, _f64p, _f64p, _f64p, C.POINTER(C.c_int)]),
     "qc_set_option": (C.c_int, [_vp, C.c_char_p, C.c_int64]),
     "qc_k2_plan_stats": (C.c_int, [C.c_int, C.c_size_t, _u64p, _u64p, _f64p, _u64p, _f64p]),

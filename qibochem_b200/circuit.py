@@ -207,6 +207,9 @@ class Circuit:
         rt = get_runtime()
         st = rt.state(self.nqubits)
         if initial_state is None:
+            if hasattr(st, "prepare_state"):  # one native call: K0 + K1 (a single launch on a small register)
+                st.prepare_state(prog.basis_index, prog.xmask, prog.zmask, prog.angle)
+                return st
             st.set_basis_state(prog.basis_index)
         else:
             psi = np.asarray(initial_state, dtype=np.complex128).reshape(-1)

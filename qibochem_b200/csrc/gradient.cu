@@ -20,7 +20,7 @@ namespace qc {
 
 void plan_rotation_runs(size_t R, const uint64_t* xs, const uint64_t* zs, std::vector<std::pair<size_t, size_t>>& out);
 int apply_rotations_to(qc_state* h, double2* target, size_t R, const uint64_t* xmask, const uint64_t* zmask,
-                       const double* angle, int k1_mode, int* n_passes_out);
+                       const double* angle, int k1_mode, int* n_passes_out, long long basis_index = -1);
 
 constexpr int kHGroupsPerLaunch = 16;
 constexpr int kHTermsPerLaunch = 1024;

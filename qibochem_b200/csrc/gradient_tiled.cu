@@ -84,6 +84,32 @@ __device__ __forceinline__ double hp_sign(double v, unsigned par) {
     return __longlong_as_double(__double_as_longlong(v) ^ ((long long)(par & 1u) << 63));
 }
 
+// acc[j] += (+-bsum) * psi_{partner of element j} for the 16 elements of a thread.  XJ = the x-mask's bits on the element
+// bits: a template parameter, so that the partner of element j sits at the COMPILE-TIME offset (j ^ XJ) * 256 slots from
+// the thread's base and the 16 loads need no address arithmetic (the kernel was issue-bound on it: 48 of ~200
+// instructions per x-mask).  walsh = 0: no signs at all; else the sign of element j is bit j.
+template <int XJ>
+__device__ __forceinline__ void hp_apply_re(double2 (&acc)[kHpElems], const double2* __restrict__ base, double bsum,
+                                            uint32_t walsh) {
+    if (walsh == 0u) {
+#pragma unroll
+        for (int j = 0; j < kHpElems; ++j) {
+            const double2 v = base[(j ^ XJ) * kHpThreads];
+            acc[j].x = fma(bsum, v.x, acc[j].x);
+            acc[j].y = fma(bsum, v.y, acc[j].y);
+        }
+    } else {
+        const double bneg = -bsum;
+#pragma unroll
+        for (int j = 0; j < kHpElems; ++j) {
+            const double2 v = base[(j ^ XJ) * kHpThreads];
+            const double wj = (walsh >> j) & 1u ? bneg : bsum;
+            acc[j].x = fma(wj, v.x, acc[j].x);
+            acc[j].y = fma(wj, v.y, acc[j].y);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kHpThreads, 2)
     hpsi_tiled_kernel(const double2* __restrict__ psi, double2* __restrict__ lam, int n, const HpPass pass,
                       const uint4* __restrict__ units, int accumulate) {
@@ -171,6 +197,17 @@ __global__ void __launch_bounds__(kHpThreads, 2)
                     const uint4 sraw = blob[s0];
                     const double bsum = segment_sum(sraw);
                     const uint32_t walsh = sraw.z;
+                    if (type == 0) {
+                        const double2* pb = tile + (t ^ (x_loc & 0xffu));
+#define QC_HP_CASE(X) case X: hp_apply_re<X>(acc, pb, bsum, walsh); break;
+                        switch (xj) {
+                            QC_HP_CASE(0) QC_HP_CASE(1) QC_HP_CASE(2) QC_HP_CASE(3) QC_HP_CASE(4) QC_HP_CASE(5) QC_HP_CASE(6)
+                            QC_HP_CASE(7) QC_HP_CASE(8) QC_HP_CASE(9) QC_HP_CASE(10) QC_HP_CASE(11) QC_HP_CASE(12)
+                            QC_HP_CASE(13) QC_HP_CASE(14) QC_HP_CASE(15)
+                        }
+#undef QC_HP_CASE
+                        continue;
+                    }
                     if (walsh == 0u) {
 #pragma unroll
                         for (int j = 0; j < kHpElems; ++j) {

@@ -129,20 +129,43 @@ __global__ void __launch_bounds__(kThreads) rot_diag_kernel(double2* __restrict_
 constexpr int kSmallMaxQubits = 13;   // 2^13 x 16 B = 128 KB of shared memory
 constexpr int kSmallThreads = 1024;
 
+// STAGED = true: the run descriptors and their (cos, sin) tables sit in shared memory behind the state (they fit for the
+// LiH / BeH2-sized programs); from global memory the two dependent loads per run (descriptor, then table entry) cost
+// ~1.5 us per run with nothing to hide them behind -- one CTA, one run at a time.
+template <bool STAGED>
 __global__ void __launch_bounds__(kSmallThreads, 1)
     rot_small_kernel(double2* __restrict__ psi, int n, int n_runs, const RotDesc* __restrict__ descs,
-                     const double2* __restrict__ table) {
+                     const double2* __restrict__ table, uint32_t n_table, long long basis_index) {
     extern __shared__ __align__(16) unsigned char small_raw[];
     double2* s = reinterpret_cast<double2*>(small_raw);
     const uint32_t dim = 1u << n, npairs = dim >> 1;
-    for (uint32_t i = threadIdx.x; i < dim; i += kSmallThreads) s[i] = psi[i];
+    // basis_index >= 0: start from that basis state (K0 fused into the launch); -1: from the amplitudes in HBM;
+    // -2: from the all-zero vector (a shard that does not hold the basis state)
+    if (basis_index == -1) {
+        for (uint32_t i = threadIdx.x; i < dim; i += kSmallThreads) s[i] = psi[i];
+    } else {
+        for (uint32_t i = threadIdx.x; i < dim; i += kSmallThreads)
+            s[i] = make_double2((long long)i == basis_index ? 1.0 : 0.0, 0.0);
+    }
+    const double2* tab_base = table;
+    const RotDesc* dsc = descs;
+    if (STAGED) {
+        double2* stab = s + dim;
+        uint64_t* sdesc = reinterpret_cast<uint64_t*>(stab + n_table);
+        for (uint32_t i = threadIdx.x; i < n_table; i += kSmallThreads) stab[i] = table[i];
+        const uint64_t* gdesc = reinterpret_cast<const uint64_t*>(descs);
+        const uint32_t n_units = (uint32_t)n_runs * (uint32_t)(sizeof(RotDesc) / 8);
+        for (uint32_t i = threadIdx.x; i < n_units; i += kSmallThreads) sdesc[i] = gdesc[i];
+        tab_base = stab;
+        dsc = reinterpret_cast<const RotDesc*>(sdesc);
+    }
     __syncthreads();
     for (int r = 0; r < n_runs; ++r) {
-        const RotDesc d = descs[r];  // warp-uniform loads
-        const double2* tab = table + d.table_off;
+        const RotDesc d = dsc[r];  // warp-uniform loads
+        const double2* tab = tab_base + d.table_off;
         if (d.x == 0) {
             for (uint32_t i = threadIdx.x; i < dim; i += kSmallThreads) {
-                const double2 cs = __ldg(&tab[d.sup_mask ? gather_bits(i, d.sup_mask) : 0u]);
+                const double2 cs = tab[d.sup_mask ? gather_bits(i, d.sup_mask) : 0u];
                 const double ms = -flip_sign(cs.y, i, d.z0);
                 const double2 a = s[i];
                 s[i] = make_double2(cs.x * a.x - ms * a.y, cs.x * a.y + ms * a.x);
@@ -151,7 +174,7 @@ __global__ void __launch_bounds__(kSmallThreads, 1)
             for (uint32_t p = threadIdx.x; p < npairs; p += kSmallThreads) {
                 const uint32_t i = (uint32_t)insert_zero_bit(p, d.hb), j = i ^ (uint32_t)d.x;
                 const double2 a = s[i], b = s[j];
-                const double2 cs = __ldg(&tab[d.sup_mask ? gather_bits(i, d.sup_mask) : 0u]);
+                const double2 cs = tab[d.sup_mask ? gather_bits(i, d.sup_mask) : 0u];
                 const double f = flip_sign(cs.y, i, d.z0);
                 const double2 wb = cmul(d.war, d.wai, b);
                 const double2 wa = cmul(d.wbr, d.wbi, a);
@@ -516,11 +539,11 @@ void plan_rotation_runs(size_t R, const uint64_t* xs, const uint64_t* zs, std::v
 
 // Applies the rotations to `target` (a shard-sized array of this handle: psi itself or the scratch array).
 int apply_rotations_to(qc_state* h, double2* target, size_t R, const uint64_t* xmask, const uint64_t* zmask,
-                       const double* angle, int k1_mode, int* n_passes_out) {
+                       const double* angle, int k1_mode, int* n_passes_out, long long basis_index) {
     std::vector<Run> runs;
     plan_runs(R, xmask, zmask, runs);
 
-    if (h->n <= kSmallMaxQubits && k1_mode == 0 && runs.size() >= 2) {
+    if (h->n <= kSmallMaxQubits && k1_mode == 0 && (runs.size() >= 2 || basis_index != -1)) {
         // ---- small register: every run of the call in ONE launch, state in shared memory
         size_t total_entries = 0;
         for (const Run& g : runs) total_entries += (size_t)1 << __builtin_popcountll(g.sup);
@@ -563,12 +586,18 @@ int apply_rotations_to(qc_state* h, double2* target, size_t R, const uint64_t* x
         }
         QC_CHECK(cudaMemcpyAsync(h->arena.dev, h->arena.host, bytes_desc + total_entries * sizeof(double2), cudaMemcpyHostToDevice, h->stream));
         h->h2d_bytes += bytes_desc + total_entries * sizeof(double2);
-        const size_t smem = (size_t)h->dim * sizeof(double2);
-        QC_CHECK(cudaFuncSetAttribute(rot_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
+        static_assert(sizeof(RotDesc) % 8 == 0, "RotDesc is copied in 8-byte units");
+        const size_t smem_state = (size_t)h->dim * sizeof(double2);
+        const size_t smem_staged = smem_state + total_entries * sizeof(double2) + runs.size() * sizeof(RotDesc);
+        const bool staged = smem_staged <= 220 * 1024;
+        const size_t smem = staged ? smem_staged : smem_state;
+        auto kernel = staged ? rot_small_kernel<true> : rot_small_kernel<false>;
+        QC_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
         {
             LaunchScope ls(h, kK1Rotation, 32.0 * (double)h->dim * (double)runs.size());
-            rot_small_kernel<<<1, kSmallThreads, smem, h->stream>>>(target, h->n, (int)runs.size(), (const RotDesc*)h->arena.dev,
-                                                                  (const double2*)((const char*)h->arena.dev + bytes_desc));
+            kernel<<<1, kSmallThreads, smem, h->stream>>>(target, h->n, (int)runs.size(), (const RotDesc*)h->arena.dev,
+                                                          (const double2*)((const char*)h->arena.dev + bytes_desc), (uint32_t)total_entries,
+                                                          basis_index);
         }
         QC_CHECK(cudaGetLastError());
         if (n_passes_out) *n_passes_out = 1;
@@ -862,5 +891,25 @@ extern "C" int qc_apply_pauli_rotations(qc_state* h, size_t R, const uint64_t* x
     for (size_t r = 0; r < R; ++r)
         QC_REQUIRE(xmask[r] < h->dim && zmask[r] < h->dim, "qc_apply_pauli_rotations: mask has bits outside the shard");
     QC_CHECK(cudaSetDevice(h->device));
-    return apply_rotations_to(h, h->psi, R, xmask, zmask, angle, h->k1_mode, n_passes_out);
+    return apply_rotations_to(h, h->psi, R, xmask, zmask, angle, h->k1_mode, n_passes_out, -1);
+}
+
+extern "C" int qc_prepare_state(qc_state* h, uint64_t basis_index, int has_one, size_t R, const uint64_t* xmask,
+                                const uint64_t* zmask, const double* angle, int* n_passes_out) {
+    using namespace qc;
+    QC_REQUIRE(h, "qc_prepare_state: null handle");
+    if (n_passes_out) *n_passes_out = 0;
+    QC_REQUIRE(!has_one || basis_index < h->dim, "qc_prepare_state: index out of range");
+    QC_REQUIRE(R == 0 || (xmask && zmask && angle), "qc_prepare_state: null array");
+    for (size_t r = 0; r < R; ++r)
+        QC_REQUIRE(xmask[r] < h->dim && zmask[r] < h->dim, "qc_prepare_state: mask has bits outside the shard");
+    QC_CHECK(cudaSetDevice(h->device));
+    if (h->n <= kSmallMaxQubits && h->k1_mode == 0 && R > 0) {
+        // small register: basis state + the whole program in ONE launch
+        h->prof.bytes[kK0Init] += 16.0 * (double)h->dim;
+        return apply_rotations_to(h, h->psi, R, xmask, zmask, angle, 0, n_passes_out, has_one ? (long long)basis_index : -2);
+    }
+    if (qc_set_basis_state(h, basis_index, has_one)) return 1;
+    if (R == 0) return 0;
+    return apply_rotations_to(h, h->psi, R, xmask, zmask, angle, h->k1_mode, n_passes_out, -1);
 }

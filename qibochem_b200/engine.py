@@ -98,6 +98,20 @@ class DeviceState:
         self.last_passes = passes.value
         return passes.value
 
+    def prepare_state(self, index: int, xmask, zmask, angle, has_one: bool = True) -> int:
+        """K0 + K1 in one native call: basis state ``index``, then the rotation program (one launch on a small register)."""
+        x, z, a = _u64(xmask), _u64(zmask), _f64(angle)
+        if not (x.shape == z.shape == a.shape and x.ndim == 1):
+            raise ValueError("xmask, zmask and angle must be 1-d arrays of equal length")
+        passes = C.c_int(0)
+        _native.check(
+            self._lib.qc_prepare_state(self._h, C.c_uint64(int(index)), int(bool(has_one)), x.size, _ptr(x, C.c_uint64),
+                                       _ptr(z, C.c_uint64), _ptr(a, C.c_double), C.byref(passes)),
+            "qc_prepare_state",
+        )  # fmt: skip
+        self.last_passes = passes.value
+        return passes.value
+
     # -- K2 ---------------------------------------------------------------------------------------------------
     def expectation(self, xmask, zmask, coeff, per_term: bool = False):
         x, z, c = _u64(xmask), _u64(zmask), _f64(coeff)
