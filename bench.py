@@ -57,7 +57,8 @@ def parse_args():
     ap.add_argument("--no-parity-check", action="store_true", help="N > 1: skip the oracle / 1-GPU-twin parity checks")
     ap.add_argument("--no-ladder-point", action="store_true", help="skip the 32-qubit single-GPU point of the weak-scaling ladder")
     ap.add_argument("--no-small-configs", action="store_true", help="skip BASELINE configs 1-3 (4 / 12 / 14 qubits)")
-    ap.add_argument("--no-full-stream", action="store_true", help="skip the extra full-UCCSD-stream measurement")
+    ap.add_argument("--no-full-stream", action="store_true", help="N = 1: skip the extra full-UCCSD-stream measurement")
+    ap.add_argument("--full-stream", action="store_true", help="N > 1: add one step with the complete UCCSD rotation stream (60-80 s)")
     return ap.parse_args()
 
 

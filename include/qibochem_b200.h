@@ -110,6 +110,11 @@ int qc_hpsi(qc_state* h, size_t T, const uint64_t* hxmask, const uint64_t* hzmas
 int qc_lambda_inner(qc_state* h, double* re_out, double* im_out);
 int qc_gradient_backward(qc_state* h, size_t R, const uint64_t* xmask, const uint64_t* zmask, const double* angle,
                          double* grad_out);
+/* Host-only (no GPU needed): shape of the tiled H|psi> plan of a term list.  stats_out: 8 x uint64 {passes, x-masks
+ * served by tiles, segments, terms, largest number of x-masks in one pass, leftover terms (sweep kernel), x-masks
+ * with a single segment, of those with an empty sign word}. */
+int qc_hpsi_plan_stats(int n_local_qubits, size_t T, const uint64_t* hxmask, const uint64_t* hzmask, const double* coeff,
+                       uint64_t* stats_out);
 /* <psi|psi> over this shard. */
 int qc_norm2(qc_state* h, double* out);
 

@@ -37,6 +37,7 @@ SIGNATURES = {
     "qc_hpsi": (C.c_int, [_vp, C.c_size_t, _u64p, _u64p, _f64p, C.c_int]),
     "qc_lambda_inner": (C.c_int, [_vp, _f64p, _f64p]),
     "qc_gradient_backward": (C.c_int, [_vp, C.c_size_t, _u64p, _u64p, _f64p, _f64p]),
+    "qc_hpsi_plan_stats": (C.c_int, [C.c_int, C.c_size_t, _u64p, _u64p, _f64p, _u64p]),
     "qc_norm2": (C.c_int, [_vp, _f64p]),
     "qc_sample": (C.c_int, [_vp, C.c_uint64, C.c_uint64, C.c_size_t, C.c_uint64, C.c_uint64, _vp, C.c_int, _f64p]),
     "qc_parity_sums": (C.c_int, [_vp, _vp, _vp, C.c_size_t, C.c_int, _u64p, C.c_size_t, _i64p]),

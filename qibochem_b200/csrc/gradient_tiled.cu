@@ -271,8 +271,9 @@ __global__ void __launch_bounds__(kHpThreads, 2)
 // ---------------------------------------------------------------------------------------------------------------
 // host
 // ---------------------------------------------------------------------------------------------------------------
-static HpPlan* build_hp_plan(qc_state* h, size_t T, const uint64_t* hx, const uint64_t* hz, const double* hc) {
-    const int n = h->n;
+// h == nullptr: host-only planning (statistics; no device upload)
+static HpPlan* build_hp_plan(qc_state* h, int n, size_t T, const uint64_t* hx, const uint64_t* hz, const double* hc,
+                             uint64_t* stats = nullptr) {
     HostPlan* kp = build_host_plan(n, T, hx, hz, hc);  // only its tile sets are used
     if (!kp) return nullptr;
     std::vector<uint64_t> sets;
@@ -433,7 +434,29 @@ static HpPlan* build_hp_plan(qc_state* h, size_t T, const uint64_t* hx, const ui
         }
         flush();
     }
-    {
+    if (stats) {
+        // {passes, x-masks, segments, terms, largest number of x-masks in a pass, leftover terms, x-masks with ONE
+        //  segment, of those with an empty Walsh word}
+        uint64_t n_seg = 0, n_term = 0, max_g = 0, single = 0, plain = 0;
+        for (const HpPass& ps : plan->passes) {
+            n_seg += ps.n_segs;
+            n_term += ps.blob_units - ps.n_groups - ps.n_segs;
+            max_g = std::max<uint64_t>(max_g, ps.n_groups);
+            for (uint32_t g = 0; g < ps.n_groups; ++g) {
+                HpGroup gr;
+                memcpy(&gr, &units[ps.blob_off + g], 16);
+                if (gr.n_seg_re + gr.n_seg_im == 1) {
+                    HpSeg sg;
+                    memcpy(&sg, &units[ps.blob_off + gr.first_seg], 16);
+                    single += 1;
+                    plain += sg.walsh == 0;
+                }
+            }
+        }
+        const uint64_t v[8] = {plan->passes.size(), plan->n_groups, n_seg, n_term, max_g, plan->left_x.size(), single, plain};
+        for (int i = 0; i < 8; ++i) stats[i] = v[i];
+    }
+    if (h) {
         const size_t bytes = std::max<size_t>(units.size(), 1) * sizeof(Unit16);
         if (cudaMalloc((void**)&plan->d_units, bytes) != cudaSuccess ||
             (!units.empty() && cudaMemcpy(plan->d_units, units.data(), units.size() * sizeof(Unit16), cudaMemcpyHostToDevice) != cudaSuccess)) {
@@ -461,7 +484,7 @@ int hpsi_tiled(qc_state* h, size_t T, const uint64_t* hx, const uint64_t* hz, co
         QC_CHECK(cudaStreamSynchronize(h->stream));  // the old plan may still be read by in-flight passes
         delete h->hp_plan;
         h->hp_plan = nullptr;
-        plan = build_hp_plan(h, T, hx, hz, hc);
+        plan = build_hp_plan(h, h->n, T, hx, hz, hc);
         QC_REQUIRE(plan != nullptr, "qc_hpsi: could not build the tiled plan");
         h->hp_plan = plan;
     }
@@ -490,3 +513,20 @@ int hpsi_tiled(qc_state* h, size_t T, const uint64_t* hx, const uint64_t* hz, co
 }
 
 }  // namespace qc
+
+// Host-only (no GPU needed): plans the tiled H|psi> of a term list and reports its shape.  stats_out: 8 x uint64
+// {passes, x-masks served by tiles, segments, terms, largest number of x-masks in one pass, leftover terms (sweep
+//  kernel), x-masks with a single segment, of those with an empty Walsh word}.
+extern "C" int qc_hpsi_plan_stats(int n_local_qubits, size_t T, const uint64_t* xmask, const uint64_t* zmask,
+                                  const double* coeff, uint64_t* stats_out) {
+    using namespace qc;
+    QC_REQUIRE(xmask && zmask && coeff && stats_out, "qc_hpsi_plan_stats: null argument");
+    QC_REQUIRE(n_local_qubits >= kTileBits && n_local_qubits <= 40, "qc_hpsi_plan_stats: needs 12..40 local qubits");
+    for (size_t k = 0; k < T; ++k)
+        QC_REQUIRE((xmask[k] >> n_local_qubits) == 0 && (zmask[k] >> n_local_qubits) == 0,
+                   "qc_hpsi_plan_stats: mask has bits outside the shard");
+    HpPlan* p = build_hp_plan(nullptr, n_local_qubits, T, xmask, zmask, coeff, stats_out);
+    QC_REQUIRE(p != nullptr, "qc_hpsi_plan_stats: planner failed");
+    delete p;
+    return 0;
+}
