@@ -218,6 +218,7 @@ def main_sharded(args, n: int, nelec: int, out) -> None:
     clock_info = clocks.stop() if clocks else None
     swaps = st.n_swaps - swaps0
 
+    norm2 = st.norm2()  # size-independent property of the full-size run (no oracle reaches 33-35 qubits): unitarity
     main_swap_seconds, main_swap_bytes = ex.swap_seconds, ex.swap_bytes
     e2e = measure_e2e_public_api(st, local, wl, n, world, rank, local_rank, 1, dist, torch)
     full = None
@@ -262,6 +263,7 @@ def main_sharded(args, n: int, nelec: int, out) -> None:
             "k2_passes_per_step": st.last_sweeps,
             "cpu_baseline": None,
             "parity_check": parity,
+            "norm_check": {"qubits": n, "norm2_after_the_last_step": norm2, "abs_err": abs(norm2 - 1.0), "ok": bool(abs(norm2 - 1.0) < 1e-10)},
             "full_uccsd_stream": full,
         }  # fmt: skip
         out.emit(line)

@@ -490,3 +490,67 @@ def test_givens_circuit_and_gates():
 
     circ.run_on_device()
     assert get_runtime().state(n).last_passes == 1
+
+
+@pytest.mark.parametrize("builder", ["qeb", "givens"])
+def test_vqe_loop_over_gates_that_lower_to_several_rotations(builder):
+    """qeb / givens ansatz with several excitations: `set_parameters` AFTER the first execution (the cached program's
+    fast path, a numpy vector as an optimiser passes it) must update every rotation of a gate with that gate's parameter
+    -- it used to broadcast per rotation and fail; energies against the oracle's execution of the lowered program."""
+    A = _api()
+    from qibochem_b200.ansatz import givens_circuit, qeb_circuit
+
+    n = 6
+    build = qeb_circuit if builder == "qeb" else givens_circuit
+    circ = A["hf_circuit"](n, 2)
+    for exc, th in (([0, 1, 2, 3], 0.1), ([0, 4], 0.2), ([1, 2, 4, 5], 0.3)):
+        circ += build(n, exc, th)
+    rng = np.random.default_rng(3)
+    strings = ("Z0", "X0 X1", "Y1 Y4", "Z2 Z5", "X0 Z1 X2", "Y0 Z1 Z2 Y3", "X2 X3 Y4 Y5")
+    terms = {tuple((int(op[1:]), op[0]) for op in s.split()): float(rng.normal()) for s in strings}
+    terms[()] = 0.37
+    const, xs, zs, cs = F.masks_from_terms(n, terms)
+    ham = A["SymbolicHamiltonian"].from_index_masks(n, xs, zs, cs, constant=const)
+
+    def oracle_energy():
+        prog = circ.program()
+        psi = np.zeros(2**n, dtype=complex)
+        psi[prog.basis_index] = 1.0
+        for x, z, a in zip(prog.xmask.tolist(), prog.zmask.tolist(), prog.angle.tolist()):
+            psi = O.apply_pauli_rotation(psi, x, z, a)
+        return O.expectation_masks(psi, xs, zs, cs, const)
+
+    e0 = ham.expectation(circ)
+    assert abs(e0 - oracle_energy()) < 1e-10
+    for trial in range(3):
+        new = rng.uniform(-1, 1, size=len(circ.get_parameters()))
+        circ.set_parameters(new)  # numpy vector: fast path on the cached program
+        fresh = circ.copy()  # compiled from the gates' own parameters: must agree with the patched program
+        assert np.allclose(fresh.program().angle, circ.program().angle, rtol=0, atol=0)
+        e = ham.expectation(circ)
+        assert abs(e - oracle_energy()) < 1e-10
+        assert abs(e - e0) > 1e-6
+    assert [p[0] for p in circ.get_parameters()] == pytest.approx(list(new))
+
+
+def test_runtime_adopts_a_caller_owned_state():
+    """`Runtime.adopt` / `forget`: the public API runs on a DeviceState the caller allocated (bench.py's e2e leg), no
+    private attribute involved; adopting does not close the previous owner's state."""
+    A = _api()
+    from qibochem_b200.engine import DeviceState
+    from qibochem_b200.runtime import get_runtime
+
+    n = 5
+    rt = get_runtime()
+    circ = A["hf_circuit"](n, 2) + A["ucc_circuit"](n, [0, 1, 3, 4], 0.3)
+    ham = A["SymbolicHamiltonian"](A["Z"](0) * A["Z"](3) + 0.5 * A["X"](1) * A["X"](4) + 0.25)
+    e_ref = ham.expectation(circ)
+    with DeviceState(n) as mine:
+        rt.adopt(mine)
+        assert rt.state(n) is mine
+        assert abs(ham.expectation(circ) - e_ref) < 1e-13
+        assert abs(mine.norm2() - 1.0) < 1e-13  # the circuit really ran on the adopted state
+        rt.forget(mine)
+        assert rt.state(n) is not mine
+        assert abs(mine.norm2() - 1.0) < 1e-13  # still alive: forget() does not close it
+    assert abs(ham.expectation(circ) - e_ref) < 1e-13

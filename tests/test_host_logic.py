@@ -432,3 +432,30 @@ def test_givens_sign_pinned_by_reference_decomposition_on_every_basis_state(exci
         assert np.abs(got - ref).max() < 1e-13
         moved += int(np.abs(ref - psi0).max() > 1e-3)
     assert moved >= 3  # the rotated pair of determinants and the random state really move
+
+
+@pytest.mark.parametrize("n,T", [(13, 700), (16, 3000), (20, 20000)])
+def test_hpsi_tiled_plan_covers_every_term(native_lib, n, T):
+    """Host-only shape of the tiled H|psi> plan (gradient_tiled.cu): every term is served exactly once -- by a tile pass
+    or by the sweep fall-back -- and an x-mask never has fewer segments than 1 nor more than 16 (4 element bits)."""
+    import ctypes as C
+
+    from qibochem_b200 import synthetic
+
+    hx, hz, hc, _ = synthetic.molecular_like_hamiltonian(n, T)
+    rng = np.random.default_rng(n)
+    wide = np.array([int(sum(1 << int(b) for b in rng.choice(n, size=13, replace=False))) for _ in range(5)], dtype=np.uint64)
+    hx = np.concatenate([hx, wide])  # x-masks too wide for a 12-bit tile: sweep fall-back
+    hz = np.concatenate([hz, rng.integers(0, 2**n, size=5, dtype=np.uint64)])
+    hc = np.concatenate([hc, rng.normal(size=5)])
+    stats = np.zeros(8, dtype=np.uint64)
+    u64p, f64p = C.POINTER(C.c_uint64), C.POINTER(C.c_double)
+    rc = native_lib.qc_hpsi_plan_stats(n, hx.size, hx.ctypes.data_as(u64p), hz.ctypes.data_as(u64p), hc.ctypes.data_as(f64p),
+                                       stats.ctypes.data_as(u64p))  # fmt: skip
+    assert rc == 0
+    passes, xmasks, segs, terms, max_groups, left, single, plain = (int(v) for v in stats)
+    n_wide_terms = int(np.isin(hx, np.unique(wide)).sum())
+    assert left == n_wide_terms and terms + left == hx.size
+    assert xmasks == np.unique(hx).size - np.unique(wide).size
+    assert xmasks <= segs <= 16 * 2 * xmasks and plain <= single <= xmasks
+    assert 1 <= passes and max_groups >= xmasks / passes
