@@ -55,6 +55,7 @@ def parse_args():
     ap.add_argument("--cpu-sample-qubits", type=int, default=24)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity-check", action="store_true", help="N > 1: skip the oracle / 1-GPU-twin parity checks")
+    ap.add_argument("--no-gradient", action="store_true", help="skip the adjoint-gradient measurement (one call, ~30 s at 30 qubits)")
     ap.add_argument("--no-ladder-point", action="store_true", help="skip the 32-qubit single-GPU point of the weak-scaling ladder")
     ap.add_argument("--no-small-configs", action="store_true", help="skip BASELINE configs 1-3 (4 / 12 / 14 qubits)")
     ap.add_argument("--no-full-stream", action="store_true", help="N = 1: skip the extra full-UCCSD-stream measurement")
@@ -363,6 +364,7 @@ def main():
         cpu = cpu_reference_sample(wl, args.cpu_sample_qubits)
         cpu["fit"] = cpu_scaling_points()
     real_path = measure_real_path(wl, st, stream) if n == 30 else None
+    gradient = None if args.no_gradient else measure_gradient(wl, st, stream, ms_per_step)
     small = None if args.no_small_configs else measure_small_configs()
     ladder = None
     if not args.no_ladder_point and n == 30 and args.rotations == 1024 and torch.cuda.get_device_properties(0).total_memory > 100e9:
@@ -376,7 +378,8 @@ def main():
         "passes_per_step": {"k1_rotation_passes": passes, "k2_xmask_sweeps": sweeps},
         "wall_ms_per_step": 1e3 * wall / args.steps,
         "clocks": clock_info, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
-        "full_uccsd_stream": full, "real_amplitude_fast_path": real_path, "small_configs": small, "weak_ladder_32q_1gpu": ladder,
+        "full_uccsd_stream": full, "real_amplitude_fast_path": real_path, "gradient_30q" if n == 30 else "gradient": gradient,
+        "small_configs": small, "weak_ladder_32q_1gpu": ladder,
     }  # fmt: skip
     out.emit(line)
 
@@ -464,6 +467,33 @@ def measure_real_path(wl, st, stream) -> dict:
     st.set_option("k2_real", 0)
     return {"taken": bool(taken), "ms_per_step": ms, "expectation_ms": ms_k2, "evals_per_sec": 1e3 / ms, "energy": e,
             "note": "same workload as the headline; identical energy to 1e-12; not the headline because the arithmetic is real, not complex128"}  # fmt: skip
+
+
+def measure_gradient(wl, st, stream, energy_ms: float) -> dict:
+    """Adjoint gradient of the benchmark energy with respect to ALL rotation angles (reference caller:
+    qibo.derivative.parameter_shift, doc/source/tutorials/adaptive.rst:46-61, two energy evaluations per parameter):
+    forward execution, lambda = H psi through tiles (K6T), backward walk over the fused runs.  ONE timed call (the plan of
+    the tiled H|psi> is built inside it, ~0.5 s of host time)."""
+    import torch
+
+    st.set_basis_state(wl["hf"])
+    st.apply_pauli_rotations(wl["rx"], wl["rz"], wl["ra"])
+    st.profile_reset()
+    st.profile_enable(True)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    t0 = time.perf_counter()
+    e, grad = st.energy_gradient(wl["rx"], wl["rz"], wl["ra"], wl["hx"], wl["hz"], wl["hc"])
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    prof = st.profile()
+    st.profile_enable(False)
+    ms = ev0.elapsed_time(ev1)
+    return {"parameters": int(grad.size), "ms": ms, "wall_ms": 1e3 * wall, "in_units_of_one_energy": ms / energy_ms,
+            "parameter_shift_would_need_energies": 2 * int(grad.size), "energy": wl["const"] + e,
+            "max_abs_gradient": float(np.abs(grad).max()),
+            "device_ms": {k: round(v["ms"], 1) for k, v in prof.items() if v["launches"]}}  # fmt: skip
 
 
 def measure_ladder_point(n: int, args, stream) -> dict:
