@@ -54,7 +54,8 @@ struct HpSeg {             // 16 bytes
     uint32_t pad;
 };
 struct HpTerm {            // 16 bytes
-    uint64_t z;            // bits 0..55: z outside the tile (index-bit positions, n <= 40); bits 56..63: z on the 8 thread bits
+    uint64_t z;            // bits 0..39: z outside the tile (index-bit positions, n <= 40); bits 40..55 (Re-type terms): the
+                           // 2^M signs of the term's z on the element bits inside x; bits 56..63: z on the 8 thread bits
     double d;              // signed coefficient (conventions of hpsi_kernel)
 };
 static_assert(sizeof(HpGroup) == 16 && sizeof(HpSeg) == 16 && sizeof(HpTerm) == 16, "blob units");
@@ -84,28 +85,66 @@ __device__ __forceinline__ double hp_sign(double v, unsigned par) {
     return __longlong_as_double(__double_as_longlong(v) ^ ((long long)(par & 1u) << 63));
 }
 
-// acc[j] += (+-bsum) * psi_{partner of element j} for the 16 elements of a thread.  XJ = the x-mask's bits on the element
-// bits: a template parameter, so that the partner of element j sits at the COMPILE-TIME offset (j ^ XJ) * 256 slots from
-// the thread's base and the 16 loads need no address arithmetic (the kernel was issue-bound on it: 48 of ~200
-// instructions per x-mask).  walsh = 0: no signs at all; else the sign of element j is bit j.
-template <int XJ>
-__device__ __forceinline__ void hp_apply_re(double2 (&acc)[kHpElems], const double2* __restrict__ base, double bsum,
-                                            uint32_t walsh) {
-    if (walsh == 0u) {
-#pragma unroll
-        for (int j = 0; j < kHpElems; ++j) {
-            const double2 v = base[(j ^ XJ) * kHpThreads];
-            acc[j].x = fma(bsum, v.x, acc[j].x);
-            acc[j].y = fma(bsum, v.y, acc[j].y);
+// All Re-type (even nY) terms of one x-mask.  XJ = the x-mask's bits on the 4 element bits, a template parameter, so that
+//  (a) the partner of element j sits at the COMPILE-TIME offset (j ^ XJ) * 256 slots from the thread's base: the 16
+//      loads need no address arithmetic;
+//  (b) the terms of an x-mask differ in z on the x-mask's OWN bits (the Y sites of XXYY / YYXX / ...), and a random quad
+//      has 1.3 of its four bits among the element bits, which used to split it into 2.7 "segments" of 16 signed
+//      additions each.  Instead: a SUB-SEGMENT collects the terms that agree on the element bits OUTSIDE x (one Walsh
+//      word for the 16 elements), each term carries the 2^M signs of its z on the M = popcount(XJ) element bits INSIDE x,
+//      V[u] = sum_k (+-)c_k over u = 0 .. 2^M - 1 is formed once, and element j takes V[pext(j, XJ)] -- a compile-time
+//      index -- times its Walsh sign.
+__host__ __device__ constexpr int hp_pext4(int j, int mask) {
+    int out = 0, pos = 0;
+    for (int b = 0; b < 4; ++b)
+        if ((mask >> b) & 1) {
+            out |= ((j >> b) & 1) << pos;
+            ++pos;
         }
-    } else {
-        const double bneg = -bsum;
+    return out;
+}
+
+template <int XJ>
+__device__ __forceinline__ void hp_group_re(double2 (&acc)[kHpElems], const double2* __restrict__ base,
+                                            const uint4* __restrict__ blob, uint32_t first_sub, uint32_t n_sub, uint32_t sw_lo,
+                                            uint32_t sw_hi) {
+    constexpr int M = ((XJ >> 0) & 1) + ((XJ >> 1) & 1) + ((XJ >> 2) & 1) + ((XJ >> 3) & 1);
+    constexpr int NV = 1 << M;
+    auto sub_values = [&](const uint4& sraw, double (&V)[NV]) {
 #pragma unroll
-        for (int j = 0; j < kHpElems; ++j) {
-            const double2 v = base[(j ^ XJ) * kHpThreads];
-            const double wj = (walsh >> j) & 1u ? bneg : bsum;
-            acc[j].x = fma(wj, v.x, acc[j].x);
-            acc[j].y = fma(wj, v.y, acc[j].y);
+        for (int u = 0; u < NV; ++u) V[u] = 0.0;
+        const uint4* tp = blob + sraw.x;
+        for (uint32_t k = 0; k < sraw.y; ++k) {
+            const uint4 q = tp[k];
+            const double c = hp_sign(__hiloint2double((int)q.w, (int)q.z), __popc((sw_lo & q.x) ^ (sw_hi & q.y)));
+            const uint32_t wy = q.y >> 8;  // bits 8..23 of the high word: the term's 2^M signs (bit u)
+#pragma unroll
+            for (int u = 0; u < NV; ++u) V[u] += NV == 1 ? c : hp_sign(c, wy >> u);
+        }
+    };
+    // one apply per sub-segment (a quad has one; a hopping group a handful: its extra partner loads are cheaper than
+    // a 16-entry weight array next to V and the accumulators in 128 registers)
+    for (uint32_t s = 0; s < n_sub; ++s) {
+        const uint4 sraw = blob[first_sub + s];
+        double V[NV];
+        sub_values(sraw, V);
+        const uint32_t walsh = sraw.z;
+        if (walsh == 0u) {
+#pragma unroll
+            for (int j = 0; j < kHpElems; ++j) {
+                const double2 v = base[(j ^ XJ) * kHpThreads];
+                const double wj = V[hp_pext4(j, XJ)];
+                acc[j].x = fma(wj, v.x, acc[j].x);
+                acc[j].y = fma(wj, v.y, acc[j].y);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < kHpElems; ++j) {
+                const double2 v = base[(j ^ XJ) * kHpThreads];
+                const double wj = hp_sign(V[hp_pext4(j, XJ)], walsh >> j);
+                acc[j].x = fma(wj, v.x, acc[j].x);
+                acc[j].y = fma(wj, v.y, acc[j].y);
+            }
         }
     }
 }
@@ -170,95 +209,43 @@ __global__ void __launch_bounds__(kHpThreads, 2)
             const uint32_t x_loc = graw.x;
             const double2* partner = tile + (t ^ (x_loc & 0xffu));
             const uint32_t xj = x_loc >> 8;
-#pragma unroll 1
-            for (int type = 0; type < 2; ++type) {
-                const uint32_t s0 = graw.y + (type ? (graw.z & 0xffffu) : 0u);
-                const uint32_t ns = type ? (graw.z >> 16) : (graw.z & 0xffffu);
-                if (ns == 0) continue;
-                // signed sum of a segment's coefficients for this (tile origin, thread)
-                auto segment_sum = [&](const uint4& sraw) {
-                    const uint4* tp = blob + sraw.x;
-                    double b0 = 0.0, b1 = 0.0;
-                    uint32_t k = 0;
-                    for (; k + 1 < sraw.y; k += 2) {
-                        const uint4 q0 = tp[k], q1 = tp[k + 1];
-                        b0 += hp_sign(__hiloint2double((int)q0.w, (int)q0.z), __popc((sw_lo & q0.x) ^ (sw_hi & q0.y)));
-                        b1 += hp_sign(__hiloint2double((int)q1.w, (int)q1.z), __popc((sw_lo & q1.x) ^ (sw_hi & q1.y)));
+            // ---- Re-type terms (even nY): everything in one templated call selected by the element-bit part of x
+            {
+                const uint32_t n_sub = graw.z & 0xffffu;
+                if (n_sub) {
+                    const double2* pb = tile + (t ^ (x_loc & 0xffu));
+#define QC_HP_CASE(X) case X: hp_group_re<X>(acc, pb, blob, graw.y, n_sub, sw_lo, sw_hi); break;
+                    switch (xj) {
+                        QC_HP_CASE(0) QC_HP_CASE(1) QC_HP_CASE(2) QC_HP_CASE(3) QC_HP_CASE(4) QC_HP_CASE(5) QC_HP_CASE(6)
+                        QC_HP_CASE(7) QC_HP_CASE(8) QC_HP_CASE(9) QC_HP_CASE(10) QC_HP_CASE(11) QC_HP_CASE(12)
+                        QC_HP_CASE(13) QC_HP_CASE(14) QC_HP_CASE(15)
                     }
-                    if (k < sraw.y) {
-                        const uint4 q0 = tp[k];
-                        b0 += hp_sign(__hiloint2double((int)q0.w, (int)q0.z), __popc((sw_lo & q0.x) ^ (sw_hi & q0.y)));
-                    }
-                    return b0 + b1;
-                };
-                if (ns == 1) {
-                    // ONE segment (the common case: the element bits are chosen where the z-masks are emptiest): the 16
-                    // weights are +-bsum, no weight array; with an empty Walsh word not even a sign
-                    const uint4 sraw = blob[s0];
-                    const double bsum = segment_sum(sraw);
-                    const uint32_t walsh = sraw.z;
-                    if (type == 0) {
-                        const double2* pb = tile + (t ^ (x_loc & 0xffu));
-#define QC_HP_CASE(X) case X: hp_apply_re<X>(acc, pb, bsum, walsh); break;
-                        switch (xj) {
-                            QC_HP_CASE(0) QC_HP_CASE(1) QC_HP_CASE(2) QC_HP_CASE(3) QC_HP_CASE(4) QC_HP_CASE(5) QC_HP_CASE(6)
-                            QC_HP_CASE(7) QC_HP_CASE(8) QC_HP_CASE(9) QC_HP_CASE(10) QC_HP_CASE(11) QC_HP_CASE(12)
-                            QC_HP_CASE(13) QC_HP_CASE(14) QC_HP_CASE(15)
-                        }
 #undef QC_HP_CASE
-                        continue;
-                    }
-                    if (walsh == 0u) {
-#pragma unroll
-                        for (int j = 0; j < kHpElems; ++j) {
-                            const double2 v = partner[(uint32_t)(j ^ xj) * kHpThreads];
-                            if (type == 0) {
-                                acc[j].x = fma(bsum, v.x, acc[j].x);
-                                acc[j].y = fma(bsum, v.y, acc[j].y);
-                            } else {
-                                acc[j].x = fma(-bsum, v.y, acc[j].x);
-                                acc[j].y = fma(bsum, v.x, acc[j].y);
-                            }
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < kHpElems; ++j) {
-                            const double2 v = partner[(uint32_t)(j ^ xj) * kHpThreads];
-                            const double wj = hp_sign(bsum, walsh >> j);
-                            if (type == 0) {
-                                acc[j].x = fma(wj, v.x, acc[j].x);
-                                acc[j].y = fma(wj, v.y, acc[j].y);
-                            } else {
-                                acc[j].x = fma(-wj, v.y, acc[j].x);
-                                acc[j].y = fma(wj, v.x, acc[j].y);
-                            }
-                        }
-                    }
-                    continue;
                 }
+            }
+            // ---- Im-type terms (odd nY; none in a molecular Hamiltonian): segments keyed by the whole z on the element bits
+            const uint32_t ns_im = graw.z >> 16;
+            if (ns_im) {
+                const uint32_t s0 = graw.y + (graw.z & 0xffffu);
                 double w[kHpElems];
 #pragma unroll
                 for (int j = 0; j < kHpElems; ++j) w[j] = 0.0;
-                for (uint32_t s = 0; s < ns; ++s) {
+                for (uint32_t s = 0; s < ns_im; ++s) {
                     const uint4 sraw = blob[s0 + s];  // first_term, n_terms, walsh
-                    const double bsum = segment_sum(sraw);
+                    const uint4* tp = blob + sraw.x;
+                    double bsum = 0.0;
+                    for (uint32_t k = 0; k < sraw.y; ++k) {
+                        const uint4 q = tp[k];
+                        bsum += hp_sign(__hiloint2double((int)q.w, (int)q.z), __popc((sw_lo & q.x) ^ (sw_hi & q.y)));
+                    }
 #pragma unroll
                     for (int j = 0; j < kHpElems; ++j) w[j] += hp_sign(bsum, sraw.z >> j);
                 }
-                if (type == 0) {
 #pragma unroll
-                    for (int j = 0; j < kHpElems; ++j) {
-                        const double2 v = partner[(uint32_t)(j ^ xj) * kHpThreads];
-                        acc[j].x = fma(w[j], v.x, acc[j].x);
-                        acc[j].y = fma(w[j], v.y, acc[j].y);
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < kHpElems; ++j) {
-                        const double2 v = partner[(uint32_t)(j ^ xj) * kHpThreads];
-                        acc[j].x = fma(-w[j], v.y, acc[j].x);
-                        acc[j].y = fma(w[j], v.x, acc[j].y);
-                    }
+                for (int j = 0; j < kHpElems; ++j) {
+                    const double2 v = partner[(uint32_t)(j ^ xj) * kHpThreads];
+                    acc[j].x = fma(-w[j], v.y, acc[j].x);
+                    acc[j].y = fma(w[j], v.x, acc[j].y);
                 }
             }
         }
@@ -405,7 +392,24 @@ static HpPlan* build_hp_plan(qc_state* h, int n, size_t T, const uint64_t* hx, c
                     const uint32_t zl = to_local(hz[tix]);
                     tm.z = (hz[tix] & ~S) | ((uint64_t)(zl & 0xffu) << 56);
                     tm.d = type ? -hc[tix] * ((((ny - 1) >> 1) & 1) ? -1.0 : 1.0) : hc[tix] * (((ny >> 1) & 1) ? -1.0 : 1.0);
-                    by_zj[zl >> 8].push_back(tm);
+                    uint32_t key = zl >> 8;
+                    if (type == 0) {
+                        // Re-type: sub-segment = z on the element bits OUTSIDE x; the part inside x becomes 2^M sign bits
+                        const uint32_t xj = go.hdr.x_loc >> 8, inside = key & xj;
+                        key &= ~xj;
+                        uint32_t yk = 0;
+                        int pos = 0, m = 0;
+                        for (int b = 0; b < 4; ++b)
+                            if ((xj >> b) & 1u) {
+                                yk |= ((inside >> b) & 1u) << pos;
+                                ++pos, ++m;
+                            }
+                        uint64_t wy = 0;
+                        for (uint32_t u = 0; u < (1u << m); ++u)
+                            if (__builtin_popcount(u & yk) & 1) wy |= 1ull << u;
+                        tm.z |= wy << 40;  // bits 40..55: unused by z_outer (n <= 40 qubits) and by the thread bits (56..63)
+                    }
+                    by_zj[key].push_back(tm);
                 }
                 for (auto& kv : by_zj) {
                     HpSeg sg;
