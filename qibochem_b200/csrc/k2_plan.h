@@ -28,7 +28,7 @@ QC_HD inline uint32_t k2_swizzle(uint32_t t) { return t ^ ((t >> 3) & 7u) ^ ((t 
 
 // Per-pass "blob": [TRBlock headers][record stream], staged ONCE per CTA into shared memory next to the tile, so
 // that walking the records costs broadcast LDS instead of dependent global loads.
-constexpr uint32_t kBlobCapUnits = 2752;            // 43 KB of 16-byte units per pass: tile 64 KB + blob -> 2 CTAs/SM; real path: 32 KB + blob -> 3
+constexpr uint32_t kBlobCapUnits = 2816;            // 44 KB of 16-byte units per pass (tile 64 KB + blob: 2 CTAs/SM)
 
 struct TPass {             // kernel parameter (constant bank)
     uint64_t s_mask;       // the kTileBits index bits of the tile (always contains bit 0)
