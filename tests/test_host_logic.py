@@ -459,3 +459,78 @@ def test_hpsi_tiled_plan_covers_every_term(native_lib, n, T):
     assert xmasks == np.unique(hx).size - np.unique(wide).size
     assert xmasks <= segs <= 16 * 2 * xmasks and plain <= single <= xmasks
     assert 1 <= passes and max_groups >= xmasks / passes
+
+
+def test_accelerators_need_one_process_per_gpu(monkeypatch):
+    """`Circuit(n, accelerators=...)` -- qibo's multi-device argument, which the reference's builders forward
+    (src/qibochem/ansatz/ansatz.py:120, :341) -- asks for a world of that many ranks: a single process is told how to
+    launch instead of silently running on one GPU; one device is always fine."""
+    monkeypatch.delenv("WORLD_SIZE", raising=False)
+    monkeypatch.delenv("RANK", raising=False)
+    c = hf_circuit(4, 2, accelerators={"/GPU:0": 1})
+    assert c.nqubits == 4
+    with pytest.raises(RuntimeError, match="torchrun --nproc-per-node 2"):
+        ucc_circuit(4, [0, 1, 2, 3], 0.1, accelerators={"/GPU:0": 1, "/GPU:1": 1})
+    with pytest.raises(NotImplementedError):
+        Circuit(4, density_matrix=True)
+
+
+class _NullShard:
+    """Stand-in shard that only records what the layout logic asks of it."""
+
+    def __init__(self):
+        self.term_calls, self.last_sweeps = [], 0
+
+    def set_basis_state(self, index, has_one=True):
+        pass
+
+    def apply_pauli_rotations(self, x, z, a):
+        return 0
+
+    def expectation(self, x, z, c):
+        self.term_calls.append((np.array(x), np.array(z), np.array(c)))
+        return float(np.sum(c))
+
+
+class _NullExchanger:
+    def __init__(self):
+        self.swaps = []
+
+    def swap(self, global_k, local_pos, with_scratch=False):
+        self.swaps.append((global_k, local_pos))
+
+    def allreduce_sum(self, v):
+        return v
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_planner_guided_layouts_serve_every_term_once(native_lib, world):
+    """ShardedState.expectation with layouts priced by the tile planner (host-only): every term reaches the local shard
+    exactly once, with masks inside the shard and the rank sign of its global z bits folded into the coefficient; the
+    layout sequence is cached (second evaluation: same calls, no planning)."""
+    from qibochem_b200 import synthetic
+    from qibochem_b200.sharded import ShardedState
+
+    n, rank = 21, world - 1
+    g = world.bit_length() - 1
+    hx, hz, hc, _ = synthetic.molecular_like_hamiltonian(n, 20000)
+    shard, ex = _NullShard(), _NullExchanger()
+    st = ShardedState(n, rank, world, shard, ex, min_swap_pos=4)
+    assert st._plan_stats is not None
+    st.set_basis_state(5)
+    total = st.expectation(hx, hz, hc)
+    calls = shard.term_calls
+    assert sum(len(c[0]) for c in calls) == hx.size and 1 <= len(calls) <= 6
+    for x, z, c in calls:
+        assert int(x.max()) < 2 ** (n - g) and int(z.max()) < 2 ** (n - g)
+    # |coefficients| are preserved, signs only flip through the rank bits: the multiset of |c| is the Hamiltonian's
+    got = np.sort(np.abs(np.concatenate([c[2] for c in calls])))
+    assert np.array_equal(got, np.sort(np.abs(hc)))
+    assert abs(total - sum(float(np.sum(c[2])) for c in calls)) < 1e-12
+    n_calls, n_cache = len(calls), len(st._layout_cache)
+    assert n_cache >= 1
+    st.set_basis_state(5)
+    st.expectation(hx, hz, hc)
+    assert len(shard.term_calls) == 2 * n_calls and len(st._layout_cache) == n_cache
+    for a, b in zip(shard.term_calls[:n_calls], shard.term_calls[n_calls:]):
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[2], b[2])
