@@ -517,6 +517,7 @@ def test_planner_guided_layouts_serve_every_term_once(native_lib, world):
     shard, ex = _NullShard(), _NullExchanger()
     st = ShardedState(n, rank, world, shard, ex, min_swap_pos=4)
     assert st._plan_stats is not None
+    st._use_planner = True  # opt-in rule (QC_SHARD_LAYOUT=planner)
     st.set_basis_state(5)
     total = st.expectation(hx, hz, hc)
     calls = shard.term_calls

@@ -216,7 +216,7 @@ def test_frequencies_bit_exact(DeviceState, bits):
         assert np.array_equal(k, vals) and np.array_equal(c, counts)
 
 
-@pytest.mark.parametrize("n", [3, 7, 13, 16])
+@pytest.mark.parametrize("n", [3, 7, 13, 16, 18])  # <= 16: full CDF + a thread per shot; 18: chunk sums + a warp per shot
 def test_sampling_inverse_cdf_matches_oracle(DeviceState, n):
     """Same Philox uniforms + same probabilities => same indices (except shots that land within rounding of a
     bin edge), in Z, X and Y bases."""
