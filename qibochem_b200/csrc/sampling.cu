@@ -250,6 +250,42 @@ __global__ void __launch_bounds__(kThreads) prob_kernel(const double2* __restric
     }
 }
 
+// |<i| B |psi>|^2 for the product basis change B = H on the bits of xm, H S^dagger on the bits of ym (<= kFusedBasisBits
+// of them), straight from psi: amplitude_i = 2^{-m/2} sum_s (-1)^{popc(i & s)} (-i)^{popc(s & ym)} psi_{i with the rotated
+// bits replaced by s}.  Replaces the scratch copy + one gate pass per rotated qubit + the |.|^2 pass of a small register
+// by ONE launch (a QWC group of a molecular Hamiltonian rotates <= 4 qubits).
+constexpr int kFusedBasisBits = 6;
+struct BasisBits {
+    int m;
+    int pos[kFusedBasisBits];
+};
+
+__global__ void __launch_bounds__(kThreads) rotated_prob_kernel(const double2* __restrict__ psi, uint32_t dim, uint32_t xm,
+                                                                uint32_t ym, const BasisBits bb, double* __restrict__ p) {
+    const uint32_t rot = xm | ym;
+    const double scale = 1.0 / (double)(1u << bb.m);
+    for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < dim; i += gridDim.x * kThreads) {
+        const uint32_t base = i & ~rot;
+        double re = 0.0, im = 0.0;
+        for (uint32_t k = 0; k < (1u << bb.m); ++k) {
+            uint32_t sbits = 0;
+            for (int j = 0; j < bb.m; ++j) sbits |= ((k >> j) & 1u) << bb.pos[j];
+            const double2 a = psi[base | sbits];
+            const bool neg = __popc(i & sbits) & 1;
+            double vr = a.x, vi = a.y;
+            switch (__popc(sbits & ym) & 3) {  // times (-i)^{nY}
+                case 1: vr = a.y, vi = -a.x; break;
+                case 2: vr = -a.x, vi = -a.y; break;
+                case 3: vr = -a.y, vi = a.x; break;
+                default: break;
+            }
+            re += neg ? -vr : vr;
+            im += neg ? -vi : vi;
+        }
+        p[i] = (re * re + im * im) * scale;
+    }
+}
+
 __global__ void __launch_bounds__(kThreads) sample_cdf_kernel(const double* __restrict__ cdf, uint32_t dim, uint64_t n_shots,
                                                               uint64_t seed, uint64_t shot_offset, uint64_t* __restrict__ samples) {
     const double total = cdf[dim - 1];
@@ -399,7 +435,9 @@ int qc_sample(qc_state* h, uint64_t x_basis_mask, uint64_t y_basis_mask, size_t 
     QC_REQUIRE(n_shots == 0 || samples_out, "qc_sample: null output");
     QC_CHECK(cudaSetDevice(h->device));
     const double2* src = h->psi;
-    if (x_basis_mask | y_basis_mask) {
+    const int n_rot = __builtin_popcountll(x_basis_mask | y_basis_mask);
+    const bool fused_small = h->n <= kCdfMaxQubits && n_rot <= kFusedBasisBits;
+    if ((x_basis_mask | y_basis_mask) && !fused_small) {
         if (!h->scratch_psi) QC_CHECK(cudaMalloc(&h->scratch_psi, h->dim * sizeof(double2)));
         QC_CHECK(cudaMemcpyAsync(h->scratch_psi, h->psi, h->dim * sizeof(double2), cudaMemcpyDeviceToDevice, h->stream));
         const double r = 0.70710678118654752440;
@@ -418,7 +456,16 @@ int qc_sample(qc_state* h, uint64_t x_basis_mask, uint64_t y_basis_mask, size_t 
         {
             LaunchScope ls(h, kK5Sampling, 16.0 * (double)h->dim);
             const int nb = (int)std::min<uint64_t>((h->dim + kThreads - 1) / kThreads, (uint64_t)h->sm_count * kCtasPerSm);
-            prob_kernel<<<nb, kThreads, 0, h->stream>>>(src, h->dim, h->d_partials);
+            if (fused_small && n_rot > 0) {
+                BasisBits bb;
+                bb.m = 0;
+                for (int b = 0; b < h->n; ++b)
+                    if (((x_basis_mask | y_basis_mask) >> b) & 1ull) bb.pos[bb.m++] = b;
+                rotated_prob_kernel<<<nb, kThreads, 0, h->stream>>>(h->psi, (uint32_t)h->dim, (uint32_t)x_basis_mask,
+                                                                    (uint32_t)y_basis_mask, bb, h->d_partials);
+            } else {
+                prob_kernel<<<nb, kThreads, 0, h->stream>>>(src, h->dim, h->d_partials);
+            }
         }
         QC_CHECK(cudaGetLastError());
         {

@@ -825,3 +825,30 @@ def test_real_amplitude_fast_path(DeviceState, n):
         assert not st.took_real_path()
         st.set_option("k2_real", 0)
         assert abs(st.expectation(hx, hz, hc) - e_c) < 1e-13
+
+
+@pytest.mark.parametrize("n,n_rot", [(5, 2), (12, 4), (14, 6), (14, 7)])
+def test_sampling_small_register_fused_basis_change(DeviceState, n, n_rot):
+    """Small registers (<= 16 qubits) with <= 6 rotated qubits compute |<i|B|psi>|^2 in one launch straight from psi
+    (no scratch copy, no gate passes); 7 rotated qubits take the gate path.  Same Philox uniforms + the oracle's
+    probabilities => same indices, except shots within rounding of a bin edge."""
+    psi = random_state(n, 7 * n + n_rot)
+    rng = np.random.default_rng(100 * n + n_rot)
+    bits = rng.choice(n, size=n_rot, replace=False)
+    xb = int(sum(1 << int(b) for b in bits[: n_rot // 2]))
+    yb = int(sum(1 << int(b) for b in bits[n_rot // 2 :]))
+    basis = {n - 1 - b: ("X" if (xb >> b) & 1 else "Y") for b in range(n) if ((xb | yb) >> b) & 1}
+    rot = O.run_gates(n, O.measurement_basis_gates(basis), psi.copy())
+    cdf = np.cumsum(np.abs(rot) ** 2)
+    n_shots, seed = 30_000, 99 + n
+    target = O.philox_uniform53(n_shots, seed) * cdf[-1]
+    ref_idx = np.minimum(np.searchsorted(cdf, target, side="right"), 2**n - 1)
+    with DeviceState(n) as st:
+        st.from_numpy(psi)
+        got, total = st.sample(xb, yb, n_shots, seed, return_total=True)
+        assert abs(total - 1.0) < 1e-12
+        assert np.array_equal(st.to_numpy(), psi)
+    edge = np.minimum(np.abs(cdf[ref_idx] - target), np.abs(cdf[np.maximum(ref_idx - 1, 0)] - target))
+    mismatch = got != ref_idx.astype(np.uint64)
+    assert np.all(edge[mismatch] < 1e-12)
+    assert mismatch.mean() < 1e-3
