@@ -10,10 +10,13 @@
 //
 // A CTA of 256 threads stages the 4096 amplitudes of a tile (64 KB, cp.async); thread t owns the 16 tile elements
 // e_j = t | j << 8 and keeps their lambda in registers for the whole tile.  The sign of a term splits into
-// (tile origin, thread bits) -- one POPC per term, thread and tile -- and the 4 "j" bits, whose 16 parities come from a
-// Walsh word; terms of an x-mask that agree on the j bits form a SEGMENT and are summed before they touch the 16
-// elements.  The partner amplitudes psi_{e ^ x} come from shared memory (conflict-free: XOR with x permutes a warp's
-// 32 consecutive slots), so the kernel is bound by those LDS.128 (64 KB per x-mask and tile), not by HBM.
+// (tile origin, thread bits) -- one POPC per term, thread and tile -- and the 4 element ("j") bits.  On the element bits
+// OUTSIDE x the terms of an x-mask are grouped into SUB-SEGMENTS that share one 16-bit Walsh word; on the element bits
+// INSIDE x (the Y sites of XXYY / YYXX / ... differ there) every term carries its 2^M signs, M = the number of such
+// bits, and the 2^M partial sums are indexed at compile time (16-way switch on x's element-bit part, which also
+// makes the partner offsets compile-time constants).  The partner amplitudes psi_{e ^ x} come from shared memory
+// (conflict-free: XOR with x permutes a warp's 32 consecutive slots), so the kernel is bound by those LDS.128
+// (64 KB per x-mask and tile), not by HBM; all per-pass metadata is a blob in shared memory.
 #include <string.h>
 
 #include <algorithm>
@@ -47,10 +50,10 @@ struct HpGroup {           // 16 bytes
     uint16_t n_seg_re, n_seg_im;  // segments of Re-type (even nY) terms first
     uint32_t pad;
 };
-struct HpSeg {             // 16 bytes
+struct HpSeg {             // 16 bytes: a sub-segment (Re-type terms) or a segment (Im-type terms)
     uint32_t first_term;   // unit index inside the blob
     uint32_t n_terms;
-    uint32_t walsh;        // bit j = parity(j & z_j) of the segment's common z on the element bits
+    uint32_t walsh;        // bit j = parity(j & z_j), z_j = the common z on the element bits (Re-type: outside x only)
     uint32_t pad;
 };
 struct HpTerm {            // 16 bytes
