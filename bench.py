@@ -358,18 +358,26 @@ def main():
     roofline = build_roofline(wl, prof, args, dev_ms)
     launches = int(sum(v["launches"] for v in prof.values()))
 
-    full = None if (args.no_full_stream or args.rotations != 1024) else measure_full_stream(wl, st, stream)
+    def extra(fn, *a):
+        """The keys below are context for the headline: a failure in one of them (say, no room for the 32-qubit state)
+        is recorded in its key and must not cost the line itself."""
+        try:
+            return fn(*a)
+        except Exception as exc:  # noqa: BLE001
+            return {"error": f"{type(exc).__name__}: {exc}"}
+
+    full = None if (args.no_full_stream or args.rotations != 1024) else extra(measure_full_stream, wl, st, stream)
     cpu = None
     if not args.no_cpu_baseline:
         cpu = cpu_reference_sample(wl, args.cpu_sample_qubits)
-        cpu["fit"] = cpu_scaling_points()
-    real_path = measure_real_path(wl, st, stream) if n == 30 else None
-    gradient = None if args.no_gradient else measure_gradient(wl, st, stream, ms_per_step)
-    small = None if args.no_small_configs else measure_small_configs()
+        cpu["fit"] = extra(cpu_scaling_points)
+    real_path = extra(measure_real_path, wl, st, stream) if n == 30 else None
+    gradient = None if args.no_gradient else extra(measure_gradient, wl, st, stream, ms_per_step)
+    small = None if args.no_small_configs else extra(measure_small_configs)
     ladder = None
     if not args.no_ladder_point and n == 30 and args.rotations == 1024 and torch.cuda.get_device_properties(0).total_memory > 100e9:
         st.close()
-        ladder = measure_ladder_point(32, args, stream)
+        ladder = extra(measure_ladder_point, 32, args, stream)
     line = {
         "metric": METRIC, "value": value * 2.0 ** (n - 30), "unit": unit_for(n), "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
