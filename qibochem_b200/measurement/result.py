@@ -95,7 +95,7 @@ def expectation_from_samples(
     """
     from qibochem_b200.circuit import _next_seed
 
-    grouped_terms = _measurement_basis_rotations(hamiltonian, grouping=grouping)
+    grouped_terms, device_plan = _sampling_plan(hamiltonian, grouping, circuit.nqubits)
     if not n_shots_per_pauli_term:
         if shot_allocation is None:
             shot_allocation = allocate_shots(grouped_terms, n_shots)
@@ -105,29 +105,43 @@ def expectation_from_samples(
     total = _constant_term(hamiltonian)
     if not grouped_terms:
         return total
-    n = circuit.nqubits
     state = circuit.run_on_device()  # psi is prepared ONCE; the reference re-runs the circuit per group
     base_seed = _next_seed() if seed is None else int(seed)
-    for i, (expression, measurement_gates, _rotation_gates) in enumerate(grouped_terms):
+    for i, (xb, yb, coeffs, masks) in enumerate(device_plan):
         nshots = n_shots if n_shots_per_pauli_term else int(shot_allocation[i])
         if not nshots:
             continue
-        xb = sum(1 << (n - 1 - g.qubits[0]) for g in measurement_gates if g.basis[0] == "X")
-        yb = sum(1 << (n - 1 - g.qubits[0]) for g in measurement_gates if g.basis[0] == "Y")
         samples = state.sample(xb, yb, nshots, (base_seed + 0x9E3779B97F4A7C15 * (i + 1)) % (1 << 64), on_device=True)
-        coeffs, masks = [], []
-        for (x, z), c in expression.terms.items():
-            support = x | z
-            m, q = 0, 0
-            while support >> q:
-                if (support >> q) & 1:
-                    m |= 1 << (n - 1 - q)
-                q += 1
-            coeffs.append(complex(c).real)
-            masks.append(m)
-        sums = state.parity_sums(samples, np.array(masks, dtype=np.uint64))
-        total += float(np.dot(np.array(coeffs), sums / nshots))
+        sums = state.parity_sums(samples, masks)
+        total += float(np.dot(coeffs, sums / nshots))
     return total
+
+
+def _sampling_plan(hamiltonian, grouping, n: int):
+    """(grouped terms, per group: X-basis mask, Y-basis mask, coefficients, support masks in index-bit positions).
+    Grouping and mask construction depend only on the Hamiltonian, and an optimiser loop samples the same Hamiltonian
+    thousands of times: both are cached on the Hamiltonian object (per grouping and register size)."""
+    cache = hamiltonian.__dict__.setdefault("_sampling_plans", {})
+    key = (grouping, int(n))
+    if key not in cache:
+        grouped_terms = _measurement_basis_rotations(hamiltonian, grouping=grouping)
+        plan = []
+        for expression, measurement_gates, _rotation_gates in grouped_terms:
+            xb = sum(1 << (n - 1 - g.qubits[0]) for g in measurement_gates if g.basis[0] == "X")
+            yb = sum(1 << (n - 1 - g.qubits[0]) for g in measurement_gates if g.basis[0] == "Y")
+            coeffs, masks = [], []
+            for (x, z), c in expression.terms.items():
+                support = x | z
+                m, q = 0, 0
+                while support >> q:
+                    if (support >> q) & 1:
+                        m |= 1 << (n - 1 - q)
+                    q += 1
+                coeffs.append(complex(c).real)
+                masks.append(m)
+            plan.append((xb, yb, np.array(coeffs, dtype=np.float64), np.array(masks, dtype=np.uint64)))
+        cache[key] = (grouped_terms, plan)
+    return cache[key]
 
 
 def _group_masks(expression: PauliSum, n: int):
