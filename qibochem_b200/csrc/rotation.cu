@@ -129,6 +129,20 @@ __global__ void __launch_bounds__(kThreads) rot_diag_kernel(double2* __restrict_
 constexpr int kSmallMaxQubits = 13;   // 2^13 x 16 B = 128 KB of shared memory
 constexpr int kSmallThreads = 1024;
 
+__device__ __forceinline__ uint32_t pext32_small(uint32_t v, uint32_t mask) {
+    uint32_t out = 0, k = 0;
+    while (mask) {
+        const int b = __ffs((int)mask) - 1;
+        out |= ((v >> b) & 1u) << k;
+        ++k;
+        mask &= mask - 1u;
+    }
+    return out;
+}
+__device__ __forceinline__ double sign32(double v, int par) {
+    return __longlong_as_double(__double_as_longlong(v) ^ ((long long)(par & 1) << 63));
+}
+
 // STAGED = true: the run descriptors and their (cos, sin) tables sit in shared memory behind the state (they fit for the
 // LiH / BeH2-sized programs); from global memory the two dependent loads per run (descriptor, then table entry) cost
 // ~1.5 us per run with nothing to hide them behind -- one CTA, one run at a time.
@@ -163,19 +177,22 @@ __global__ void __launch_bounds__(kSmallThreads, 1)
     for (int r = 0; r < n_runs; ++r) {
         const RotDesc d = dsc[r];  // warp-uniform loads
         const double2* tab = tab_base + d.table_off;
-        if (d.x == 0) {
+        // a register of <= 13 qubits: all index arithmetic in 32 bits
+        const uint32_t x32 = (uint32_t)d.x, z32 = (uint32_t)d.z0, sup32 = (uint32_t)d.sup_mask;
+        if (x32 == 0u) {
             for (uint32_t i = threadIdx.x; i < dim; i += kSmallThreads) {
-                const double2 cs = tab[d.sup_mask ? gather_bits(i, d.sup_mask) : 0u];
-                const double ms = -flip_sign(cs.y, i, d.z0);
+                const double2 cs = tab[sup32 ? pext32_small(i, sup32) : 0u];
+                const double ms = -sign32(cs.y, __popc(i & z32));
                 const double2 a = s[i];
                 s[i] = make_double2(cs.x * a.x - ms * a.y, cs.x * a.y + ms * a.x);
             }
         } else {
+            const uint32_t lowmask = (1u << d.hb) - 1u;
             for (uint32_t p = threadIdx.x; p < npairs; p += kSmallThreads) {
-                const uint32_t i = (uint32_t)insert_zero_bit(p, d.hb), j = i ^ (uint32_t)d.x;
+                const uint32_t i = ((p & ~lowmask) << 1) | (p & lowmask), j = i ^ x32;
                 const double2 a = s[i], b = s[j];
-                const double2 cs = tab[d.sup_mask ? gather_bits(i, d.sup_mask) : 0u];
-                const double f = flip_sign(cs.y, i, d.z0);
+                const double2 cs = tab[sup32 ? pext32_small(i, sup32) : 0u];
+                const double f = sign32(cs.y, __popc(i & z32));
                 const double2 wb = cmul(d.war, d.wai, b);
                 const double2 wa = cmul(d.wbr, d.wbi, a);
                 s[i] = make_double2(cs.x * a.x + f * wb.x, cs.x * a.y + f * wb.y);
